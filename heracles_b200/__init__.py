@@ -1,0 +1,33 @@
+"""
+heracles_b200 -- B200-native (sm_100a) backend for the catalogue -> HEALPix map
+-> alm -> Cl hot path of Heracles; installed next to Heracles it is the
+``heracles.cuda`` backend the reference's Field layer and CLI can drive
+unchanged.
+
+Public surface (mirrors the reference interfaces of this path):
+  CudaHealpixMapper            <- heracles.healpy.HealpixMapper
+  alm2cl, angular_power_spectra <- heracles.twopoint
+  transform                    <- heracles.mapping.transform (batched over maps)
+
+There is no CPU fallback: importing the kernels' library fails loudly if
+``heracles_b200/lib/libheracles_cuda.so`` has not been built, and creating a
+context fails without a CUDA device.
+"""
+
+from ._lib import Context, HeraclesCudaError, get_context, load  # noqa: F401
+from .arrays import DeviceArray, update_metadata  # noqa: F401
+from .mapper import CudaHealpixMapper  # noqa: F401
+from .twopoint import alm2cl, alm2lmax, angular_power_spectra  # noqa: F401
+
+__all__ = [
+    "CudaHealpixMapper",
+    "DeviceArray",
+    "Context",
+    "HeraclesCudaError",
+    "alm2cl",
+    "alm2lmax",
+    "angular_power_spectra",
+    "get_context",
+    "load",
+    "update_metadata",
+]

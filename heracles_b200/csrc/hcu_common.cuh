@@ -1,0 +1,149 @@
+// hcu_common.cuh -- shared declarations of the heracles_cuda library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/heracles_cuda.h"
+
+typedef int64_t i64;
+
+void hcu_set_error(const char *fmt, ...);
+
+#define HCU_CUDA(call)                                                        \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess) {                                                  \
+      hcu_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,        \
+                    cudaGetErrorString(e_));                                  \
+      return HCU_ERR_CUDA;                                                    \
+    }                                                                         \
+  } while (0)
+
+#define HCU_CUFFT(call)                                                       \
+  do {                                                                        \
+    cufftResult r_ = (call);                                                  \
+    if (r_ != CUFFT_SUCCESS) {                                                \
+      hcu_set_error("%s:%d: %s failed: cufft error %d", __FILE__, __LINE__,   \
+                    #call, (int)r_);                                          \
+      return HCU_ERR_CUDA;                                                    \
+    }                                                                         \
+  } while (0)
+
+#define HCU_CHECK(call)                                                       \
+  do {                                                                        \
+    int s_ = (call);                                                          \
+    if (s_ != HCU_OK) return s_;                                              \
+  } while (0)
+
+#define HCU_ARG(cond, msg)                                                    \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      hcu_set_error("invalid argument: %s", msg);                             \
+      return HCU_ERR_ARG;                                                     \
+    }                                                                         \
+  } while (0)
+
+#define HCU_LAUNCH_CHECK(ctx)                                                 \
+  do {                                                                        \
+    (ctx)->n_launch++;                                                        \
+    HCU_CUDA(cudaGetLastError());                                             \
+  } while (0)
+
+// a growable device workspace
+struct hcu_buffer {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+};
+
+// per-nside tables
+struct hcu_geom {
+  i64 nside = 0;
+  int nrp = 0;           // ring pairs = 2 nside
+  double *cth = nullptr; // [nrp] cos(theta) of the north ring
+  double *sth = nullptr; // [nrp] sin(theta)
+  double *ch = nullptr;  // [nrp] cos(theta/2)
+  double *sh = nullptr;  // [nrp] sin(theta/2)
+  // Bluestein filter spectra for the polar-cap sub-FFTs of length i = 1..nside-1
+  double2 *bfilt = nullptr; // concatenated, bit-reversed FFT_M(chirp)/M
+  i64 *bfilt_off = nullptr; // [nside] offsets (device)
+  std::vector<i64> bfilt_off_h;
+};
+
+// per-(lmax, spin) recursion coefficient table
+struct hcu_coef {
+  int lmax = 0, spin = 0;
+  double *tab = nullptr; // spin 0: double2 (alpha, gamma); spin 2: double4 (alpha, alpha*beta, gamma, 0)
+  double *cm = nullptr;  // [lmax+1] start-value normalisation (mantissa), see k_legendre.cu
+};
+
+struct hcu_stage_slot {
+  double *host = nullptr; // pinned
+  double *dev = nullptr;
+  cudaEvent_t done = nullptr;
+  bool used = false;
+};
+
+struct hcu_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  i64 n_launch = 0, n_cufft = 0;
+  // staging for pageable host pages
+  static const int NSLOT = 3;
+  static const i64 SLOT_ROWS = 1 << 18;
+  static const int SLOT_COLS = 4; // lon, lat, up to 2 value rows
+  hcu_stage_slot slot[NSLOT];
+  int next_slot = 0;
+  unsigned long long *bad_rows = nullptr; // device counter
+  // workspaces
+  hcu_buffer ws_phase, ws_belt, ws_cap, ws_map, ws_alm, ws_misc, ws_state;
+  // tables
+  std::map<i64, hcu_geom> geom;
+  std::map<std::pair<int, int>, hcu_coef> coef;
+  std::map<i64, cufftHandle> belt_plan, belt_plan_inv;
+  // timing
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float sht_ms[4] = {0, 0, 0, 0};
+  double *work_counters = nullptr; // device [2]
+};
+
+int hcu_ws_reserve(hcu_ctx *ctx, hcu_buffer *b, size_t bytes);
+int hcu_get_geom(hcu_ctx *ctx, i64 nside, hcu_geom **out);
+int hcu_get_coef(hcu_ctx *ctx, int lmax, int spin, hcu_coef **out);
+
+// kernels' host launchers (defined in the k_*.cu files)
+int hcu_launch_map_values(hcu_ctx *ctx, i64 nside, int scheme, const double *lon,
+                          const double *lat, const double *values, i64 vstride,
+                          int nv, i64 n, double *maps, i64 mstride, int flags,
+                          i64 *ipix_out);
+int hcu_build_bluestein(hcu_ctx *ctx, hcu_geom *g);
+int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
+                         const double *maps, i64 map_stride,
+                         const double *ring_weights, i64 rp_lo, i64 rp_hi,
+                         double *phase);
+int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
+                         const double *phase, double *maps, i64 map_stride);
+int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c);
+int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
+                          int spin, int ncomp, const double *phase,
+                          const int32_t *mlist_dev, int nm, i64 rp_lo, i64 rp_hi,
+                          const double *fl_dev, double *alm, i64 alm_stride);
+int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
+                           int spin, int ncomp, const double *alm,
+                           i64 alm_stride, double *phase);
+
+static inline int ilog2_host(i64 v) {
+  int r = 0;
+  while (v > 1) {
+    v >>= 1;
+    ++r;
+  }
+  return r;
+}

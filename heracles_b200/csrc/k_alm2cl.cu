@@ -1,0 +1,114 @@
+// k_alm2cl.cu -- angular power spectra from alm, all pairs of a block at once.
+//
+// Replaces alm2cl (heracles/twopoint.py:63-101):
+//   C_l = [ Re(a_l0 b_l0*) + 2 sum_{m=1..l} Re(a_lm b_lm*) ] / (2l+1)
+// (the reference evaluates this as a running mean over m; the two differ by
+// rounding only, <= 2e-16 of sqrt(C_l^aa C_l^bb)).
+//
+// HBM-bound: every a_lm / b_lm is read once per tile of TA x TB spectra.
+// One thread owns one l and walks m (consecutive lanes = consecutive l =
+// consecutive addresses in the m-major layout); the m range is split across
+// blockIdx.y and partial sums are combined with RED.ADD.F64.
+#include "hcu_common.cuh"
+
+namespace {
+
+constexpr int TA = 4, TB = 4;
+
+struct ClArgs {
+  const double2 *a, *b;
+  i64 sa, sb;  // strides in complex elements
+  int na, nb, lmax_a, lmax_b, lout, msplit;
+  double *cl;
+  bool same;  // a and b are the same array with the same stride: only j >= i is computed
+};
+
+__global__ void __launch_bounds__(128) alm2cl_kernel(ClArgs p) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ia0 = (blockIdx.z / ((p.nb + TB - 1) / TB)) * TA;
+  const int ib0 = (blockIdx.z % ((p.nb + TB - 1) / TB)) * TB;
+  if (p.same && ib0 + TB - 1 < ia0) return;  // strictly lower tile of a symmetric block
+  if (l > p.lout) return;
+  // m segment of this block
+  const int mseg = (p.lout + p.msplit) / p.msplit;
+  const int m0 = blockIdx.y * mseg;
+  int m1 = m0 + mseg - 1;
+  if (m1 > l) m1 = l;
+  if (m0 > l) return;
+  double acc[TA][TB];
+#pragma unroll
+  for (int i = 0; i < TA; ++i)
+#pragma unroll
+    for (int j = 0; j < TB; ++j) acc[i][j] = 0.0;
+  for (int m = m0; m <= m1; ++m) {
+    const i64 ia = (i64)m * (2 * p.lmax_a + 1 - m) / 2 + l;
+    const i64 ib = (i64)m * (2 * p.lmax_b + 1 - m) / 2 + l;
+    // the reference's m = 0 term is alm.real * alm2.real (twopoint.py:88): imaginary
+    // parts of a_l0 (zero for real fields) are ignored
+    const double wgt = (m == 0) ? 1.0 : 2.0;
+    const double wim = (m == 0) ? 0.0 : 1.0;
+    double2 av[TA], bv[TB];
+#pragma unroll
+    for (int i = 0; i < TA; ++i)
+      av[i] = (ia0 + i < p.na) ? p.a[(i64)(ia0 + i) * p.sa + ia] : make_double2(0., 0.);
+#pragma unroll
+    for (int j = 0; j < TB; ++j)
+      bv[j] = (ib0 + j < p.nb) ? p.b[(i64)(ib0 + j) * p.sb + ib] : make_double2(0., 0.);
+#pragma unroll
+    for (int i = 0; i < TA; ++i)
+#pragma unroll
+      for (int j = 0; j < TB; ++j)
+        acc[i][j] += wgt * (av[i].x * bv[j].x + wim * (av[i].y * bv[j].y));
+  }
+  const double norm = 1.0 / (2.0 * l + 1.0);
+#pragma unroll
+  for (int i = 0; i < TA; ++i)
+#pragma unroll
+    for (int j = 0; j < TB; ++j) {
+      const int ga = ia0 + i, gb = ib0 + j;
+      if (ga < p.na && gb < p.nb) {
+        if (p.same && gb < ga) continue;
+        const double v = acc[i][j] * norm;
+        atomicAdd(p.cl + ((i64)ga * p.nb + gb) * (p.lout + 1) + l, v);
+        if (p.same && gb != ga)
+          atomicAdd(p.cl + ((i64)gb * p.nb + ga) * (p.lout + 1) + l, v);
+      }
+    }
+}
+
+}  // namespace
+
+extern "C" int hcu_alm2cl(hcu_ctx *ctx, int na, const void *a, int64_t stride_a,
+                          int lmax_a, int nb, const void *b, int64_t stride_b,
+                          int lmax_b, int lmax_out, double *cl) {
+  HCU_ARG(ctx && a && b && cl, "hcu_alm2cl: null pointer");
+  HCU_ARG(na >= 1 && nb >= 1 && lmax_a >= 0 && lmax_b >= 0 && lmax_out >= 0, "hcu_alm2cl: sizes");
+  int lout = lmax_out;
+  if (lmax_a < lout) lout = lmax_a;
+  if (lmax_b < lout) lout = lmax_b;
+  HCU_CUDA(cudaMemsetAsync(cl, 0, sizeof(double) * (size_t)na * nb * (lout + 1), ctx->stream));
+  ClArgs p;
+  p.a = (const double2 *)a;
+  p.b = (const double2 *)b;
+  p.sa = stride_a;
+  p.sb = stride_b;
+  p.na = na;
+  p.nb = nb;
+  p.lmax_a = lmax_a;
+  p.lmax_b = lmax_b;
+  p.lout = lout;
+  p.same = (a == b) && (stride_a == stride_b) && (na == nb) && (lmax_a == lmax_b);
+  p.cl = cl;
+  // enough m segments to fill the device a few times over
+  const int lblocks = (lout + 128) / 128;
+  const int tiles = ((na + TA - 1) / TA) * ((nb + TB - 1) / TB);
+  int msplit = (ctx->num_sms * 8 + lblocks * tiles - 1) / (lblocks * tiles);
+  if (msplit < 1) msplit = 1;
+  if (msplit > lout + 1) msplit = lout + 1;
+  if (msplit > 64) msplit = 64;
+  p.msplit = msplit;
+  dim3 grid(lblocks, msplit, tiles);
+  alm2cl_kernel<<<grid, 128, 0, ctx->stream>>>(p);
+  HCU_LAUNCH_CHECK(ctx);
+  return HCU_OK;
+}

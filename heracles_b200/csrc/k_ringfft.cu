@@ -1,0 +1,504 @@
+// k_ringfft.cu -- ring FFT stage of the HEALPix spherical-harmonic transform.
+//
+// Replaces the FFT half of hp.map2alm / hp.alm2map (heracles/healpy.py:183-189).
+//   * equatorial belt (2 nside + 1 rings of 4 nside pixels): cuFFT plan-many D2Z / Z2D
+//   * polar caps (rings of 4 i pixels, i = 1..nside-1): hand-written kernel.
+//     A north ring and its southern mirror are packed as ONE complex sequence
+//     z = N + i S of length 4 i, split into 4 decimated sub-sequences of length
+//     i, each transformed by a Bluestein (chirp-z) convolution on a power-of-two
+//     radix-2 FFT held in shared memory (any i, including primes).  The final
+//     radix-4 recombination, the N/S untangling, the alias fold to m <= lmax,
+//     the ring phase exp(-i m phi0) and the quadrature weight are fused into
+//     the post kernel that writes the m-major "phase" array for the Legendre
+//     stage.
+//
+// phase layout: phase[((m_idx * nrp_local + rp_local) * ncomp + c) * 4 + {0,1,2,3}]
+//   = (re+, im+, re-, im-),  + = north + south, - = north - south.
+//
+// HBM-bound: algorithmic bytes = 8 npix (map read) + 32 nrp (lmax+1) (phase write) per component.
+#include "hcu_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {  // a * conj(b)
+  return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) {
+  return make_double2(a.x + b.x, a.y + b.y);
+}
+__device__ __forceinline__ double2 csub(double2 a, double2 b) {
+  return make_double2(a.x - b.x, a.y - b.y);
+}
+// exp(-i pi x)
+__device__ __forceinline__ double2 expmipi(double x) {
+  double s, c;
+  sincospi(x, &s, &c);
+  return make_double2(c, -s);
+}
+
+// natural order in -> bit-reversed order out (decimation in frequency)
+__device__ void fft_dif(double2 *a, const double2 *tw, int M) {
+  for (int s = M >> 1, ts = 1; s >= 1; s >>= 1, ts <<= 1) {
+    for (int p = threadIdx.x; p < (M >> 1); p += blockDim.x) {
+      int k = p & (s - 1);
+      int j = ((p - k) << 1) + k;
+      double2 u = a[j], v = a[j + s];
+      a[j] = cadd(u, v);
+      a[j + s] = cmul(csub(u, v), tw[k * ts]);
+    }
+    __syncthreads();
+  }
+}
+// exact stage-by-stage inverse of fft_dif WITHOUT the 1/2 per stage
+// (bit-reversed in -> natural out); the 1/M is folded into the filter table
+__device__ void fft_dit_inv(double2 *a, const double2 *tw, int M) {
+  for (int s = 1, ts = M >> 1; s < M; s <<= 1, ts >>= 1) {
+    for (int p = threadIdx.x; p < (M >> 1); p += blockDim.x) {
+      int k = p & (s - 1);
+      int j = ((p - k) << 1) + k;
+      double2 u = a[j];
+      double2 t = cmulc(a[j + s], tw[k * ts]);
+      a[j] = cadd(u, t);
+      a[j + s] = csub(u, t);
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void make_twiddles(double2 *tw, int M) {
+  for (int k = threadIdx.x; k < (M >> 1); k += blockDim.x)
+    tw[k] = expmipi(2.0 * (double)k / (double)M);
+}
+
+// chirp c[j] = exp(-i pi j^2 / n)
+__device__ __forceinline__ double2 chirp(int j, int n) {
+  long long r = ((long long)j * j) % (2LL * n);
+  return expmipi((double)r / (double)n);
+}
+
+// Bluestein filter spectrum for sub-FFT length i: FFT_M(b)/M in bit-reversed order
+__global__ void bluestein_filter_kernel(int ilo, int M, double2 *bfilt, const i64 *off) {
+  extern __shared__ double2 smem[];
+  double2 *a = smem;
+  double2 *tw = smem + M;
+  const int n = ilo + blockIdx.x;
+  make_twiddles(tw, M);
+  for (int j = threadIdx.x; j < M; j += blockDim.x) a[j] = make_double2(0., 0.);
+  __syncthreads();
+  const double inv = 1.0 / (double)M;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    double2 c = chirp(j, n);
+    double2 b = make_double2(c.x * inv, -c.y * inv);  // conj(c)/M
+    a[j] = b;
+    if (j > 0) a[M - j] = b;
+  }
+  __syncthreads();
+  fft_dif(a, tw, M);
+  double2 *out = bfilt + off[n];
+  for (int j = threadIdx.x; j < M; j += blockDim.x) out[j] = a[j];
+}
+
+// forward: one block per (cap ring pair i, component)
+__global__ void cap_fft_fwd_kernel(int ilo, int M, i64 nside, const double *maps,
+                                   i64 map_stride, const double2 *bfilt,
+                                   const i64 *off, double2 *Y, i64 ncap) {
+  extern __shared__ double2 smem[];
+  double2 *a = smem;
+  double2 *tw = smem + M;
+  const int i = ilo + blockIdx.x;
+  const int c = blockIdx.y;
+  const i64 npix = 12 * nside * nside;
+  const i64 startN = 2LL * i * (i - 1);
+  const i64 startS = npix - startN - 4LL * i;
+  const double *mN = maps + (i64)c * map_stride + startN;
+  const double *mS = maps + (i64)c * map_stride + startS;
+  const double2 *B = bfilt + off[i];
+  double2 *Yc = Y + (i64)c * ncap + startN;
+  make_twiddles(tw, M);
+  for (int q = 0; q < 4; ++q) {
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+      double2 v = make_double2(0., 0.);
+      if (j < i) v = cmul(make_double2(mN[4 * j + q], mS[4 * j + q]), chirp(j, i));
+      a[j] = v;
+    }
+    __syncthreads();
+    fft_dif(a, tw, M);
+    for (int j = threadIdx.x; j < M; j += blockDim.x) a[j] = cmul(a[j], B[j]);
+    __syncthreads();
+    fft_dit_inv(a, tw, M);
+    for (int k = threadIdx.x; k < i; k += blockDim.x)
+      Yc[(i64)q * i + k] = cmul(a[k], chirp(k, i));
+    __syncthreads();
+  }
+}
+
+// Z[k] of the packed length-4i sequence from the four sub-FFTs
+__device__ __forceinline__ double2 cap_combine(const double2 *Yr, int i, int k) {
+  int kk = k % i;
+  double2 w1 = expmipi((double)k / (2.0 * (double)i));  // exp(-2 pi i k / (4 i))
+  double2 w2 = cmul(w1, w1);
+  double2 w3 = cmul(w2, w1);
+  double2 z = Yr[kk];
+  z = cadd(z, cmul(w1, Yr[(i64)i + kk]));
+  z = cadd(z, cmul(w2, Yr[2LL * i + kk]));
+  z = cadd(z, cmul(w3, Yr[3LL * i + kk]));
+  return z;
+}
+
+__device__ __forceinline__ void store_phase(double *phase, i64 idx, double2 n,
+                                            double2 s, double2 ph, double w) {
+  double2 p = make_double2((n.x + s.x) * w, (n.y + s.y) * w);
+  double2 q = make_double2((n.x - s.x) * w, (n.y - s.y) * w);
+  p = cmul(p, ph);
+  q = cmul(q, ph);
+  double4 *o = reinterpret_cast<double4 *>(phase + idx * 4);
+  *o = make_double4(p.x, p.y, q.x, q.y);
+}
+
+// grid: (m blocks, cap ring pairs in range); one component per launch
+__global__ void cap_post_kernel(i64 nside, int lmax, int ncomp, int comp,
+                                const double2 *Yc, const double *ring_weights,
+                                i64 rp_lo, i64 nrp_local, i64 rp_first,
+                                double *phase) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m > lmax) return;
+  const i64 rp = rp_first + blockIdx.y;
+  const int i = (int)rp + 1;
+  const int n = 4 * i;
+  const double2 *Yr = Yc + 2LL * i * (i - 1);
+  const int k = m % n;
+  const int k2 = (n - k) % n;
+  double2 z1 = cap_combine(Yr, i, k);
+  double2 z2 = cap_combine(Yr, i, k2);
+  // N[k] = (Z[k] + conj Z[n-k])/2 ; S[k] = (Z[k] - conj Z[n-k])/(2i)
+  double2 xn = make_double2(0.5 * (z1.x + z2.x), 0.5 * (z1.y - z2.y));
+  double2 d = make_double2(z1.x - z2.x, z1.y + z2.y);
+  double2 xs = make_double2(0.5 * d.y, -0.5 * d.x);
+  double w = 4.0 * 3.141592653589793238462643383279502884197 /
+             (12.0 * (double)nside * (double)nside);
+  if (ring_weights) w *= ring_weights[rp];
+  double2 ph = expmipi((double)m / (4.0 * (double)i));
+  i64 idx = ((i64)m * nrp_local + (rp - rp_lo)) * ncomp + comp;
+  store_phase(phase, idx, xn, xs, ph, w);
+}
+
+// belt: X[rb][k], rb = ring - nside (0..2 nside), k = 0..2 nside
+__global__ void belt_post_kernel(i64 nside, int lmax, int ncomp, int comp,
+                                 const double2 *X, const double *ring_weights,
+                                 i64 rp_lo, i64 nrp_local, i64 rp_first,
+                                 double *phase) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m > lmax) return;
+  const i64 rp = rp_first + blockIdx.y;
+  const i64 i = rp + 1;  // north ring number, nside <= i <= 2 nside
+  const int n4 = (int)(4 * nside);
+  const int nk = n4 / 2 + 1;
+  const i64 rbn = i - nside, rbs = 3 * nside - i;
+  int k = m % n4;
+  bool cj = k > n4 / 2;
+  if (cj) k = n4 - k;
+  double2 xn = X[rbn * nk + k];
+  double2 xs = make_double2(0., 0.);
+  if (rbs != rbn) xs = X[rbs * nk + k];
+  if (cj) {
+    xn.y = -xn.y;
+    xs.y = -xs.y;
+  }
+  double w = 4.0 * 3.141592653589793238462643383279502884197 /
+             (12.0 * (double)nside * (double)nside);
+  if (ring_weights) w *= ring_weights[rp];
+  double2 ph = make_double2(1., 0.);
+  if (((i - nside) & 1) == 0) ph = expmipi((double)m / (4.0 * (double)nside));
+  i64 idx = ((i64)m * nrp_local + (rp - rp_lo)) * ncomp + comp;
+  store_phase(phase, idx, xn, xs, ph, w);
+}
+
+// ---------------------------------------------------------------------------
+// inverse direction (synthesis): phase (b_m per ring) -> ring pixels
+// phase layout for synthesis: phase[((m * nrp + rp) * ncomp + c) * 4] = (reN, imN, reS, imS)
+// ---------------------------------------------------------------------------
+
+// belt: build the half-complex spectrum of each ring, then cuFFT Z2D
+__global__ void belt_pre_inv_kernel(i64 nside, int lmax, int ncomp, int comp,
+                                    const double *phase, double2 *X) {
+  const int n4 = (int)(4 * nside);
+  const int nk = n4 / 2 + 1;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nk) return;
+  const i64 rb = blockIdx.y;  // 0..2 nside
+  const i64 ring = rb + nside;
+  const bool south = ring > 2 * nside;
+  const i64 rp = (south ? 4 * nside - ring : ring) - 1;
+  const i64 nrp = 2 * nside;
+  const bool shifted = (((south ? 4 * nside - ring : ring) - nside) & 1) == 0;
+  // G[k] = sum over m = k (mod n4) of c_m + sum over m = -k (mod n4), m>0, of conj(c_m)
+  double2 g = make_double2(0., 0.);
+  for (int m = k; m <= lmax; m += n4) {
+    const double *p = phase + (((i64)m * nrp + rp) * ncomp + comp) * 4 + (south ? 2 : 0);
+    double2 c = make_double2(p[0], p[1]);
+    if (shifted) c = cmulc(c, expmipi((double)m / (4.0 * (double)nside)));
+    g = cadd(g, c);
+  }
+  for (int m = n4 - k; m <= lmax; m += n4) {
+    if (m == 0) continue;
+    const double *p = phase + (((i64)m * nrp + rp) * ncomp + comp) * 4 + (south ? 2 : 0);
+    double2 c = make_double2(p[0], p[1]);
+    if (shifted) c = cmulc(c, expmipi((double)m / (4.0 * (double)nside)));
+    g = cadd(g, make_double2(c.x, -c.y));
+  }
+  // f_j = sum_{k=0}^{n-1} G[k] e^{2 pi i jk/n}; Z2D computes sum over the half
+  // spectrum assuming Hermitian symmetry, which G has by construction
+  X[rb * nk + k] = g;
+}
+
+// caps: inverse of the forward scheme.  Build Z[k] = N-spectrum + i S-spectrum
+// for k = 0..4i-1, split into 4 decimated inverse sub-FFTs via Bluestein.
+// Z is the spectrum of z_j = fN_j + i fS_j: z_j = sum_k Z[k] e^{+2 pi i jk/n}.
+// With j = 4 j' + q:  z_{4j'+q} = sum_{k'=0}^{i-1} e^{2 pi i j'k'/i}
+//      [ e^{2 pi i q k'/n} sum_{s=0}^{3} Z[k' + s i] e^{2 pi i q s/4} ].
+__global__ void cap_fft_inv_kernel(int ilo, int M, i64 nside, int lmax, int ncomp,
+                                   int comp, const double *phase,
+                                   const double2 *bfilt, const i64 *off,
+                                   double *maps, i64 map_stride) {
+  extern __shared__ double2 smem[];
+  double2 *a = smem;
+  double2 *tw = smem + M;
+  const int i = ilo + blockIdx.x;
+  const int n = 4 * i;
+  const i64 npix = 12 * nside * nside;
+  const i64 nrp = 2 * nside;
+  const i64 rp = i - 1;
+  const i64 startN = 2LL * i * (i - 1);
+  const i64 startS = npix - startN - 4LL * i;
+  double *mN = maps + (i64)comp * map_stride + startN;
+  double *mS = maps + (i64)comp * map_stride + startS;
+  const double2 *B = bfilt + off[i];
+  make_twiddles(tw, M);
+  __syncthreads();
+  for (int q = 0; q < 4; ++q) {
+    // input of the sub-transform k' -> j' (inverse DFT = conj(DFT(conj(.))))
+    for (int kp = threadIdx.x; kp < M; kp += blockDim.x) {
+      double2 v = make_double2(0., 0.);
+      if (kp < i) {
+        double2 acc = make_double2(0., 0.);
+        for (int s = 0; s < 4; ++s) {
+          int k = kp + s * i;
+          // Z[k] = GN[k] + i GS[k], G[k] folded from m = k mod n and m = -k mod n
+          double2 gn = make_double2(0., 0.), gs = make_double2(0., 0.);
+          for (int m = k; m <= lmax; m += n) {
+            const double *p = phase + (((i64)m * nrp + rp) * ncomp + comp) * 4;
+            double2 e = expmipi((double)m / (4.0 * (double)i));
+            gn = cadd(gn, cmulc(make_double2(p[0], p[1]), e));
+            gs = cadd(gs, cmulc(make_double2(p[2], p[3]), e));
+          }
+          for (int m = n - k; m <= lmax; m += n) {
+            if (m == 0) continue;
+            const double *p = phase + (((i64)m * nrp + rp) * ncomp + comp) * 4;
+            double2 e = expmipi((double)m / (4.0 * (double)i));
+            double2 cn = cmulc(make_double2(p[0], p[1]), e);
+            double2 cs = cmulc(make_double2(p[2], p[3]), e);
+            gn = cadd(gn, make_double2(cn.x, -cn.y));
+            gs = cadd(gs, make_double2(cs.x, -cs.y));
+          }
+          double2 z = make_double2(gn.x - gs.y, gn.y + gs.x);
+          // e^{2 pi i q s / 4}
+          int r = (q * s) & 3;
+          double2 zr = (r == 0) ? z
+                     : (r == 1) ? make_double2(-z.y, z.x)
+                     : (r == 2) ? make_double2(-z.x, -z.y)
+                                : make_double2(z.y, -z.x);
+          acc = cadd(acc, zr);
+        }
+        // times e^{2 pi i q k'/n} = conj(exp(-i pi q k' / (2 i)))
+        double2 e = expmipi((double)(q * kp) / (2.0 * (double)i));
+        acc = cmulc(acc, e);
+        // conjugate for the inverse transform, then Bluestein pre-chirp
+        v = cmul(make_double2(acc.x, -acc.y), chirp(kp, i));
+      }
+      a[kp] = v;
+    }
+    __syncthreads();
+    fft_dif(a, tw, M);
+    for (int j = threadIdx.x; j < M; j += blockDim.x) a[j] = cmul(a[j], B[j]);
+    __syncthreads();
+    fft_dit_inv(a, tw, M);
+    for (int jp = threadIdx.x; jp < i; jp += blockDim.x) {
+      double2 r = cmul(a[jp], chirp(jp, i));
+      // undo the conjugation: z = conj(r)
+      mN[4 * jp + q] = r.x;
+      mS[4 * jp + q] = -r.y;
+    }
+    __syncthreads();
+  }
+}
+
+int bluestein_M(int i) {
+  int need = 2 * i - 1;
+  int M = 2;
+  while (M < need) M <<= 1;
+  return M;
+}
+
+int cap_threads(int M) {
+  int t = M / 2;
+  if (t < 32) t = 32;
+  if (t > 512) t = 512;
+  return t;
+}
+
+}  // namespace
+
+int hcu_build_bluestein(hcu_ctx *ctx, hcu_geom *g) {
+  const int nside = (int)g->nside;
+  g->bfilt_off_h.assign(nside + 1, 0);
+  i64 total = 0;
+  for (int i = 1; i < nside; ++i) {
+    g->bfilt_off_h[i] = total;
+    total += bluestein_M(i);
+  }
+  if (total == 0) return HCU_OK;
+  HCU_CUDA(cudaMalloc(&g->bfilt, sizeof(double2) * total));
+  HCU_CUDA(cudaMalloc(&g->bfilt_off, sizeof(i64) * (nside + 1)));
+  HCU_CUDA(cudaMemcpyAsync(g->bfilt_off, g->bfilt_off_h.data(), sizeof(i64) * (nside + 1),
+                           cudaMemcpyHostToDevice, ctx->stream));
+  int i = 1;
+  while (i < nside) {
+    int M = bluestein_M(i);
+    int ihi = i;
+    while (ihi + 1 < nside && bluestein_M(ihi + 1) == M) ++ihi;
+    size_t smem = (size_t)M * 24;
+    HCU_CUDA(cudaFuncSetAttribute(bluestein_filter_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bluestein_filter_kernel<<<ihi - i + 1, cap_threads(M), smem, ctx->stream>>>(
+        i, M, g->bfilt, g->bfilt_off);
+    HCU_LAUNCH_CHECK(ctx);
+    i = ihi + 1;
+  }
+  return HCU_OK;
+}
+
+static int get_belt_plan(hcu_ctx *ctx, std::map<i64, cufftHandle> &cache, i64 nside,
+                         bool inverse, cufftHandle *out) {
+  auto it = cache.find(nside);
+  if (it == cache.end()) {
+    cufftHandle plan;
+    int n4 = (int)(4 * nside);
+    int batch = (int)(2 * nside + 1);
+    HCU_CUFFT(cufftCreate(&plan));
+    size_t ws = 0;
+    if (!inverse)
+      HCU_CUFFT(cufftMakePlanMany(plan, 1, &n4, nullptr, 1, n4, nullptr, 1, n4 / 2 + 1,
+                                  CUFFT_D2Z, batch, &ws));
+    else
+      HCU_CUFFT(cufftMakePlanMany(plan, 1, &n4, nullptr, 1, n4 / 2 + 1, nullptr, 1, n4,
+                                  CUFFT_Z2D, batch, &ws));
+    cache[nside] = plan;
+    it = cache.find(nside);
+  }
+  HCU_CUFFT(cufftSetStream(it->second, ctx->stream));
+  *out = it->second;
+  return HCU_OK;
+}
+
+// forward ring FFT stage for ring pairs [rp_lo, rp_hi) of ncomp maps
+int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
+                         const double *maps, i64 map_stride,
+                         const double *ring_weights, i64 rp_lo, i64 rp_hi,
+                         double *phase) {
+  const i64 nside = g->nside;
+  const i64 ncap = 2 * nside * (nside - 1);
+  const i64 nrp_local = rp_hi - rp_lo;
+  const int n4 = (int)(4 * nside);
+  const int nk = n4 / 2 + 1;
+  const int mthreads = 128;
+  const unsigned mblocks = (unsigned)((lmax + 1 + mthreads - 1) / mthreads);
+
+  // ---- polar caps: ring pairs rp < nside - 1 ---------------------------------
+  i64 cap_lo = rp_lo, cap_hi = rp_hi < nside - 1 ? rp_hi : nside - 1;
+  if (cap_lo < cap_hi) {
+    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_cap, sizeof(double2) * (size_t)ncap * ncomp));
+    double2 *Y = (double2 *)ctx->ws_cap.ptr;
+    int i = (int)cap_lo + 1;
+    const int iend = (int)cap_hi;  // inclusive ring number
+    while (i <= iend) {
+      int M = bluestein_M(i);
+      int ihi = i;
+      while (ihi + 1 <= iend && bluestein_M(ihi + 1) == M) ++ihi;
+      size_t smem = (size_t)M * 24;
+      HCU_CUDA(cudaFuncSetAttribute(cap_fft_fwd_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dim3 grid(ihi - i + 1, ncomp);
+      cap_fft_fwd_kernel<<<grid, cap_threads(M), smem, ctx->stream>>>(
+          i, M, nside, maps, map_stride, g->bfilt, g->bfilt_off, Y, ncap);
+      HCU_LAUNCH_CHECK(ctx);
+      i = ihi + 1;
+    }
+    for (int c = 0; c < ncomp; ++c) {
+      dim3 grid(mblocks, (unsigned)(cap_hi - cap_lo));
+      cap_post_kernel<<<grid, mthreads, 0, ctx->stream>>>(
+          nside, lmax, ncomp, c, Y + (i64)c * ncap, ring_weights, rp_lo, nrp_local, cap_lo, phase);
+      HCU_LAUNCH_CHECK(ctx);
+    }
+  }
+
+  // ---- equatorial belt: ring pairs rp >= nside - 1 -------------------------------
+  i64 belt_lo = rp_lo > nside - 1 ? rp_lo : nside - 1, belt_hi = rp_hi;
+  if (belt_lo < belt_hi) {
+    cufftHandle plan;
+    HCU_CHECK(get_belt_plan(ctx, ctx->belt_plan, nside, false, &plan));
+    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_belt, sizeof(double2) * (size_t)nk * (2 * nside + 1)));
+    double2 *X = (double2 *)ctx->ws_belt.ptr;
+    for (int c = 0; c < ncomp; ++c) {
+      HCU_CUFFT(cufftExecD2Z(plan, const_cast<double *>(maps + (i64)c * map_stride + ncap),
+                             reinterpret_cast<cufftDoubleComplex *>(X)));
+      ctx->n_cufft++;
+      dim3 grid(mblocks, (unsigned)(belt_hi - belt_lo));
+      belt_post_kernel<<<grid, mthreads, 0, ctx->stream>>>(
+          nside, lmax, ncomp, c, X, ring_weights, rp_lo, nrp_local, belt_lo, phase);
+      HCU_LAUNCH_CHECK(ctx);
+    }
+  }
+  return HCU_OK;
+}
+
+// inverse ring FFT stage (all ring pairs), phase rows are (reN, imN, reS, imS)
+int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
+                         const double *phase, double *maps, i64 map_stride) {
+  const i64 nside = g->nside;
+  const i64 ncap = 2 * nside * (nside - 1);
+  const int n4 = (int)(4 * nside);
+  const int nk = n4 / 2 + 1;
+  // caps
+  for (int c = 0; c < ncomp; ++c) {
+    int i = 1;
+    while (i < nside) {
+      int M = bluestein_M(i);
+      int ihi = i;
+      while (ihi + 1 < nside && bluestein_M(ihi + 1) == M) ++ihi;
+      size_t smem = (size_t)M * 24;
+      HCU_CUDA(cudaFuncSetAttribute(cap_fft_inv_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cap_fft_inv_kernel<<<ihi - i + 1, cap_threads(M), smem, ctx->stream>>>(
+          i, M, nside, lmax, ncomp, c, phase, g->bfilt, g->bfilt_off, maps, map_stride);
+      HCU_LAUNCH_CHECK(ctx);
+      i = ihi + 1;
+    }
+  }
+  // belt
+  cufftHandle plan;
+  HCU_CHECK(get_belt_plan(ctx, ctx->belt_plan_inv, nside, true, &plan));
+  HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_belt, sizeof(double2) * (size_t)nk * (2 * nside + 1)));
+  double2 *X = (double2 *)ctx->ws_belt.ptr;
+  for (int c = 0; c < ncomp; ++c) {
+    dim3 grid((unsigned)((nk + 127) / 128), (unsigned)(2 * nside + 1));
+    belt_pre_inv_kernel<<<grid, 128, 0, ctx->stream>>>(nside, lmax, ncomp, c, phase, X);
+    HCU_LAUNCH_CHECK(ctx);
+    HCU_CUFFT(cufftExecZ2D(plan, reinterpret_cast<cufftDoubleComplex *>(X),
+                           maps + (i64)c * map_stride + ncap));
+    ctx->n_cufft++;
+  }
+  return HCU_OK;
+}

@@ -1,0 +1,308 @@
+"""
+``CudaHealpixMapper`` -- B200 implementation of the reference's ``HealpixMapper``
+(``heracles/healpy.py:68-209``) behind the same ``Mapper`` protocol
+(``heracles/mapper.py:33-74``): ``area``, ``create``, ``map_values``,
+``transform``, ``resample`` plus the ``nside`` / ``lmax`` / ``deconvolve``
+attributes the Field layer and the CLI read (``heracles/cli.py:162-187``).
+
+All numerics run in ``libheracles_cuda.so`` (hand-written sm_100a kernels,
+cuFFT for the equatorial rings); nothing here falls back to the CPU.
+"""
+
+from __future__ import annotations
+
+import math
+import os
+from functools import cached_property
+from typing import Any
+
+import numpy as np
+
+from . import _lib
+from .arrays import DeviceArray, update_metadata
+
+c_vp = _lib.c_vp
+
+
+def _native(arr: np.ndarray) -> np.ndarray:
+    """float64, native byte order, C-contiguous (cf. `_nativebyteorder`, healpy.py:43-55)"""
+    arr = np.asarray(arr)
+    if arr.dtype != np.float64 or arr.dtype.byteorder not in ("=", "|") or not arr.flags.c_contiguous:
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+    return arr
+
+
+def _ptr(arr: np.ndarray) -> int:
+    return arr.__array_interface__["data"][0]
+
+
+def read_pixwin_fits(path: str):
+    """
+    Minimal reader for HEALPix' ``pixel_window_n%04d.fits`` (one binary table
+    with columns TEMPERATURE, POLARIZATION of big-endian float64/float32).
+    Returns (pw_T, pw_P).
+    """
+    with open(path, "rb") as f:
+        raw = f.read()
+
+    def header(off):
+        cards = {}
+        while True:
+            block = raw[off : off + 2880]
+            off += 2880
+            for i in range(0, 2880, 80):
+                card = block[i : i + 80].decode("ascii", "replace")
+                key = card[:8].strip()
+                if key == "END":
+                    return cards, off
+                if card[8:10] == "= ":
+                    val = card[10:].split("/")[0].strip().strip("'").strip()
+                    cards[key] = val
+
+    h0, off = header(0)
+    h1, off = header(off)
+    nrow, rowlen, nfield = int(h1["NAXIS2"]), int(h1["NAXIS1"]), int(h1["TFIELDS"])
+    fmts = [h1[f"TFORM{i + 1}"] for i in range(nfield)]
+    dts = []
+    for fmt in fmts:
+        rep = int(fmt[:-1] or 1)
+        code = {"D": ">f8", "E": ">f4"}[fmt[-1]]
+        dts.append((code, rep))
+    dt = np.dtype([(f"c{i}", c, (r,)) for i, (c, r) in enumerate(dts)])
+    assert dt.itemsize == rowlen
+    tab = np.frombuffer(raw, dtype=dt, count=nrow, offset=off)
+    cols = [np.asarray(tab[f"c{i}"], dtype=np.float64).reshape(-1) for i in range(nfield)]
+    return cols[0], (cols[1] if nfield > 1 else cols[0])
+
+
+class CudaHealpixMapper:
+    """
+    Mapper for HEALPix maps on a B200.
+
+    Parameters mirror ``HealpixMapper(nside, lmax=None, *, deconvolve=None,
+    dtype=float64)``.  Additional keyword-only options:
+
+    niter : Jacobi refinement steps of the analysis; healpy's ``map2alm`` default
+        ``iter=3`` is what the reference runs (it does not pass ``iter``).
+    pixwin : explicit ``(pw_T, pw_P)`` pixel window arrays for deconvolution.
+        If omitted with ``deconvolve=True`` they are read from ``DATAPATH`` /
+        healpy's data directory (``pixel_window_n%04d.fits``) or from healpy
+        when importable; healpy's tables cannot be recomputed here.
+    device : CUDA device index (default: ``LOCAL_RANK`` or 0).
+    sync : make ``map_values`` return only when the device finished (default).
+    """
+
+    DATAPATH: str | None = None
+
+    def __init__(
+        self,
+        nside: int,
+        lmax: int | None = None,
+        *,
+        deconvolve: bool | None = None,
+        dtype: Any = np.float64,
+        niter: int = 3,
+        pixwin: Any = None,
+        pixel_weights: Any = None,
+        device: int | None = None,
+        sync: bool = True,
+        aggregate: bool = False,
+    ) -> None:
+        if lmax is None:
+            lmax = 3 * nside // 2
+        if deconvolve is None:
+            deconvolve = True
+        if np.dtype(dtype) != np.float64:
+            raise NotImplementedError("CudaHealpixMapper computes in float64 only")
+        if nside < 1 or nside & (nside - 1):
+            raise ValueError("nside must be a power of two")
+        self.__nside = int(nside)
+        self.__lmax = int(lmax)
+        self.__deconv = bool(deconvolve)
+        self.__dtype = np.dtype(dtype)
+        self.niter = int(niter)
+        self.sync = bool(sync)
+        self.aggregate = bool(aggregate)
+        self._pixwin = pixwin
+        self._pixel_weights = pixel_weights
+        self._ctx = _lib.get_context(device)
+
+    # -- reference attributes ------------------------------------------------
+    @property
+    def nside(self) -> int:
+        return self.__nside
+
+    @property
+    def lmax(self) -> int:
+        return self.__lmax
+
+    @property
+    def deconvolve(self) -> bool:
+        return self.__deconv
+
+    @property
+    def context(self) -> _lib.Context:
+        return self._ctx
+
+    @cached_property
+    def area(self) -> float:
+        """hp.nside2pixarea(nside) (healpy.py:117-122)"""
+        return 4.0 * math.pi / (12 * self.__nside * self.__nside)
+
+    @property
+    def npix(self) -> int:
+        return 12 * self.__nside * self.__nside
+
+    # -- create ---------------------------------------------------------------
+    def create(self, *dims: int, spin: int = 0):
+        """zero map(s) in managed memory + metadata (healpy.py:124-142)"""
+        m = DeviceArray.zeros(self._ctx, (*dims, self.npix), dtype=self.__dtype)
+        update_metadata(
+            m,
+            geometry="healpix",
+            kernel="healpix",
+            nside=self.__nside,
+            lmax=self.__lmax,
+            deconv=self.__deconv,
+            spin=spin,
+        )
+        return m
+
+    # -- map_values -------------------------------------------------------------
+    def map_values(self, lon, lat, data, values, spin: int = 0) -> None:
+        """data[..., ang2pix(lon, lat)] += values (healpy.py:144-160)"""
+        lon = _native(lon)
+        lat = _native(lat)
+        values = _native(values)
+        n = lon.size
+        if lat.size != n:
+            raise ValueError("lon and lat differ in size")
+        npix = self.npix
+        if data.shape[-1] != npix:
+            raise ValueError("data is not a map of this mapper")
+        nv = int(np.prod(data.shape[:-1], dtype=np.int64)) if data.ndim > 1 else 1
+        if values.size != nv * n:
+            raise ValueError("values do not match data and positions")
+        if nv > 4:
+            raise ValueError("at most 4 value rows per call")
+        dptr = data.device_ptr if isinstance(data, DeviceArray) else None
+        if dptr is None:
+            # a host array (e.g. a plain np.zeros map): map on the device, add back
+            tmp = self.create(*data.shape[:-1])
+            self.map_values(lon, lat, tmp, values, spin=spin)
+            data += tmp._host().reshape(data.shape)
+            return
+        data.to_device()
+        flags = 1 if self.aggregate else 0
+        _lib.check(
+            self._ctx.lib.hcu_map_values(
+                self._ctx.handle, self.__nside, 0, c_vp(_ptr(lon)), c_vp(_ptr(lat)), c_vp(_ptr(values)),
+                n, nv, n, c_vp(dptr), npix, flags,
+            )
+        )
+        if self.sync:
+            bad = self._ctx.bad_rows()  # synchronises
+            if bad:
+                raise ValueError("THETA is out of range [0,pi]")
+
+    # -- transform -----------------------------------------------------------------
+    def _fl(self, spin: int):
+        if not self.__deconv:
+            return None
+        pw = self._get_pixwin()[0 if spin == 0 else 1]
+        if len(pw) < self.__lmax + 1:
+            raise ValueError("pixel window shorter than lmax + 1")
+        fl = np.ones(self.__lmax + 1)
+        s = abs(spin)
+        fl[s:] /= np.asarray(pw, dtype=np.float64)[s : self.__lmax + 1]
+        return fl
+
+    def _get_pixwin(self):
+        if self._pixwin is None:
+            pw = None
+            name = "pixel_window_n%04d.fits" % self.__nside
+            paths = []
+            if self.DATAPATH:
+                paths.append(os.path.join(self.DATAPATH, name))
+            try:
+                import healpy  # noqa: F401  (optional: only for its data tables)
+
+                pw = healpy.pixwin(self.__nside, lmax=self.__lmax, pol=True)
+            except Exception:
+                for p in paths:
+                    if os.path.exists(p):
+                        pw = read_pixwin_fits(p)
+                        break
+            if pw is None:
+                raise RuntimeError(
+                    "deconvolve=True needs HEALPix' pixel window table: pass pixwin=(pw_T, pw_P), set "
+                    "CudaHealpixMapper.DATAPATH to a directory with " + name + ", or use deconvolve=False"
+                )
+            self._pixwin = pw
+        pw = self._pixwin
+        if isinstance(pw, np.ndarray) and pw.ndim == 1:
+            pw = (pw, pw)
+        return pw
+
+    def transform(self, data, spin: int = 0):
+        """map2alm (+ pixel window deconvolution), healpy.py:162-203"""
+        if spin not in (0, 2):
+            msg = f"spin-{spin} maps not yet supported"
+            raise NotImplementedError(msg)
+        md = data.dtype.metadata or {}
+        npix = self.npix
+        if data.shape[-1] != npix:
+            raise ValueError("data is not a map of this mapper")
+        lead = data.shape[:-1]
+        nmaps = int(np.prod(lead, dtype=np.int64)) if lead else 1
+        if spin == 2 and (len(lead) == 0 or lead[-1] != 2):
+            raise ValueError("spin-2 data must have shape (..., 2, npix)")
+        lmax = self.__lmax
+        nalm = (lmax + 1) * (lmax + 2) // 2
+        fl = self._fl(spin)
+        alm = DeviceArray.zeros(self._ctx, (*lead, nalm), dtype=np.complex128)
+        if isinstance(data, DeviceArray) and data.device_ptr is not None:
+            data.to_device()
+            mptr = data.device_ptr
+        else:
+            data = _native(data)
+            mptr = _ptr(data)
+        pw = self._pixel_weights
+        if pw is not None:
+            pw = _native(pw)
+        _lib.check(
+            self._ctx.lib.hcu_map2alm(
+                self._ctx.handle, self.__nside, lmax, spin, nmaps, c_vp(mptr), npix,
+                c_vp(0), c_vp(_ptr(pw) if pw is not None else 0), self.niter,
+                c_vp(_ptr(fl) if fl is not None else 0), c_vp(alm.device_ptr), nalm,
+            )
+        )
+        update_metadata(alm, **{**md, "deconv": self.__deconv})
+        return alm
+
+    # -- resample ----------------------------------------------------------------------
+    def resample(self, data):
+        """hp.ud_grade(data, nside) (healpy.py:205-209)"""
+        npix_in = data.shape[-1]
+        nside_in = int(round(math.sqrt(npix_in / 12)))
+        if 12 * nside_in * nside_in != npix_in:
+            raise ValueError("input is not a HEALPix map")
+        lead = data.shape[:-1]
+        out = DeviceArray.zeros(self._ctx, (*lead, self.npix), dtype=np.float64)
+        src = data if (isinstance(data, DeviceArray) and data.device_ptr is not None) else _native(data)
+        src2 = src.reshape(-1, npix_in)
+        out2 = out.reshape(-1, self.npix)
+        for i in range(src2.shape[0]):
+            row = src2[i]
+            sp = row.device_ptr if isinstance(row, DeviceArray) else None
+            if sp is None:
+                row = np.ascontiguousarray(row)  # kept alive until the call returns
+                sp = _ptr(row)
+            _lib.check(
+                self._ctx.lib.hcu_ud_grade(
+                    self._ctx.handle, nside_in, c_vp(sp), self.__nside, c_vp(_ptr(out2[i].view(np.ndarray)))
+                )
+            )
+        self._ctx.synchronize()
+        update_metadata(out, **(data.dtype.metadata or {}))
+        return out

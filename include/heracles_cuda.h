@@ -1,0 +1,175 @@
+/*
+ * heracles_cuda.h -- C ABI of the B200-native catalogue -> map -> alm -> Cl backend.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / numpy
+ * types.  Each entry point names the reference call site it replaces
+ * (paths relative to the heracles-ec/heracles source tree).  The Python host
+ * side (heracles_b200/) binds these with ctypes; INTEGRATION.md shows the
+ * stub a Heracles maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative hcu_status on failure;
+ *     hcu_last_error() returns a thread-local message for the last failure.
+ *     No exceptions, no aborts cross this boundary.
+ *   - "any" pointers may be pageable host, pinned host, managed or device
+ *     memory; the library detects which (cudaPointerGetAttributes) and stages
+ *     pageable host data through pinned double buffers.
+ *   - all work is queued on the context's stream (hcu_set_stream); calls are
+ *     asynchronous with respect to the host unless stated otherwise.
+ *   - maps are HEALPix RING-ordered float64, npix = 12 nside^2; alm are
+ *     complex128 in healpy's m-major layout, idx(l,m) = m(2 lmax+1-m)/2 + l,
+ *     mmax = lmax.
+ *   - there is NO CPU fallback: without a CUDA device hcu_create fails.
+ */
+#ifndef HERACLES_CUDA_H
+#define HERACLES_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HCU_VERSION 100
+
+typedef struct hcu_ctx hcu_ctx;
+
+typedef enum {
+  HCU_OK = 0,
+  HCU_ERR_CUDA = -1,     /* a CUDA / cuFFT call failed */
+  HCU_ERR_ARG = -2,      /* invalid argument */
+  HCU_ERR_NOMEM = -3,    /* allocation failed */
+  HCU_ERR_UNSUPPORTED = -4,
+  HCU_ERR_NODEVICE = -5  /* no CUDA device: the library has no CPU path */
+} hcu_status;
+
+enum { HCU_RING = 0, HCU_NEST = 1 };
+
+/* hcu_map_values flags */
+enum {
+  HCU_MAP_DEFAULT = 0,
+  HCU_MAP_AGGREGATE = 1 /* combine equal pixels inside a warp before the atomic */
+};
+
+/* ---- library / context ------------------------------------------------ */
+int hcu_version(void);
+const char *hcu_last_error(void);
+int hcu_device_count(int *count);
+int hcu_create(int device, hcu_ctx **ctx);
+int hcu_destroy(hcu_ctx *ctx);
+/* use a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = the context's own */
+int hcu_set_stream(hcu_ctx *ctx, void *cuda_stream);
+int hcu_synchronize(hcu_ctx *ctx);
+/* number of kernels of this library (and cuFFT executions) launched so far */
+int hcu_launch_count(hcu_ctx *ctx, int64_t *own_kernels, int64_t *cufft_execs);
+/* release cached workspaces (tables stay) */
+int hcu_trim(hcu_ctx *ctx);
+
+/* ---- memory ------------------------------------------------------------ */
+/* managed (unified) memory backs the ndarray that Mapper.create() returns
+ * (heracles/healpy.py:124-142): the Field layer mutates that array in place
+ * with numpy (heracles/fields.py:296,304,373,446,548), so it must be host
+ * addressable while the scatter kernels update it on the device. */
+int hcu_malloc_managed(hcu_ctx *ctx, size_t bytes, void **ptr);
+int hcu_malloc_device(hcu_ctx *ctx, size_t bytes, void **ptr);
+int hcu_malloc_pinned(hcu_ctx *ctx, size_t bytes, void **ptr);
+int hcu_free(hcu_ctx *ctx, void *ptr);
+int hcu_prefetch(hcu_ctx *ctx, const void *ptr, size_t bytes, int to_device);
+int hcu_memset_zero(hcu_ctx *ctx, void *ptr, size_t bytes);
+int hcu_memcpy(hcu_ctx *ctx, void *dst, const void *src, size_t bytes);
+
+/* ---- catalogue -> map --------------------------------------------------- */
+/* hp.ang2pix(nside, lon, lat, lonlat=True[, nest]) -- heracles/healpy.py:157,
+ * heracles/catalog/filters.py:91-94.  lon/lat in degrees.  ipix[j] = -1 for
+ * rows whose latitude is outside [-90, 90] or not finite.  Synchronous. */
+int hcu_ang2pix(hcu_ctx *ctx, int64_t nside, int scheme, const double *lon,
+                const double *lat, int64_t n, int64_t *ipix);
+
+/* HealpixMapper.map_values = hp.ang2pix + numba `_map`
+ * (heracles/healpy.py:144-160, :58-65): for each row j and each of the nv
+ * value rows v:  maps[v*map_stride + ipix_j] += values[v*value_stride + j].
+ * lon, lat, values: "any" pointers; maps: device or managed memory.
+ * Rows with invalid latitude are skipped and counted (hcu_bad_rows). */
+int hcu_map_values(hcu_ctx *ctx, int64_t nside, int scheme, const double *lon,
+                   const double *lat, const double *values,
+                   int64_t value_stride, int nv, int64_t n, double *maps,
+                   int64_t map_stride, int flags);
+/* rows skipped since the last call of this function (synchronises) */
+int hcu_bad_rows(hcu_ctx *ctx, int64_t *count);
+
+/* in-place map arithmetic used by the Field layer on the created map
+ * (heracles/fields.py:296 `pos /= nbar`, :304 `pos -= vis`, :446 `val /= wbar`) */
+int hcu_scale(hcu_ctx *ctx, double *x, int64_t n, double a);          /* x *= a        */
+int hcu_divide(hcu_ctx *ctx, double *x, int64_t n, double a);         /* x /= a        */
+int hcu_axpy(hcu_ctx *ctx, double *y, const double *x, double a, int64_t n); /* y += a x */
+int hcu_add_scalar(hcu_ctx *ctx, double *x, int64_t n, double a);     /* x += a        */
+
+/* hp.ud_grade(map, nside_out) -- heracles/healpy.py:205-209 (RING in, RING out, mean preserving) */
+int hcu_ud_grade(hcu_ctx *ctx, int64_t nside_in, const double *in,
+                 int64_t nside_out, double *out);
+
+/* ---- map -> alm ---------------------------------------------------------- */
+/* hp.map2alm(maps, lmax, pol, iter) + hp.almxfl -- heracles/healpy.py:183-196.
+ *   spin 0: nmaps independent scalar maps  -> nmaps alm rows
+ *   spin 2: nmaps must be even; rows are (Q,U) pairs -> (E,B) alm rows (the
+ *           reference's zero T map, healpy.py:174-178,198-199, is not computed)
+ *   ring_weights: NULL or float64[2*nside] multiplying 4pi/npix per ring pair
+ *   pixel_weights: NULL or float64[npix] multiplying the map before analysis
+ *   niter: Jacobi refinement steps (healpy default iter=3), alm += A(map - S(alm))
+ *   fl: NULL or float64[lmax+1]; alm[l,m] *= fl[l] (pixel-window deconvolution)
+ * maps / alm: device or managed memory ("any" for maps; host maps are copied). */
+int hcu_map2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
+                const double *maps, int64_t map_stride,
+                const double *ring_weights, const double *pixel_weights,
+                int niter, const double *fl, void *alm, int64_t alm_stride);
+
+/* hp.alm2map, the synthesis used inside map2alm's iterations (also exported) */
+int hcu_alm2map(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
+                const void *alm, int64_t alm_stride, double *maps,
+                int64_t map_stride);
+
+/* Staged transform for the multi-GPU path (no reference counterpart: the
+ * reference is single process).  Ring pairs rp = 0..2 nside-1 (north ring
+ * rp+1 with its southern mirror; rp = 2 nside - 1 is the equator).
+ *   hcu_map2phase: ring FFT stage for ring pairs [rp_lo, rp_hi) of maps that
+ *     hold AT LEAST those rings (full-size maps); writes
+ *     phase[(m * nrp_local + (rp - rp_lo)) * ncomp + c] as 4 doubles
+ *     (re+, im+, re-, im-) with +/- = north +/- south, already multiplied by
+ *     the quadrature weight and exp(-i m phi0).
+ *   hcu_phase2alm: Legendre stage for the m values mlist[0..nm) over ring
+ *     pairs [rp_lo, rp_hi); phase is indexed by position in mlist;
+ *     accumulates (+=) into alm at the global (l, m) positions. */
+int hcu_map2phase(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp,
+                  const double *maps, int64_t map_stride,
+                  const double *ring_weights, int64_t rp_lo, int64_t rp_hi,
+                  double *phase);
+int hcu_phase2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
+                  const double *phase, const int32_t *mlist, int nm,
+                  int64_t rp_lo, int64_t rp_hi, const double *fl, void *alm,
+                  int64_t alm_stride);
+
+/* ---- alm -> Cl ------------------------------------------------------------ */
+/* alm2cl(alm, alm2, lmax=lmax) -- heracles/twopoint.py:63-101, as a block:
+ *   cl[(i*nb + j)*(lout+1) + l] = sum_m (2 - delta_m0) Re(a_i,lm conj b_j,lm) / (2l+1),
+ *   lout = min(lmax_out, lmax_a, lmax_b); a, b may have different lmax. */
+int hcu_alm2cl(hcu_ctx *ctx, int na, const void *a, int64_t stride_a,
+               int lmax_a, int nb, const void *b, int64_t stride_b, int lmax_b,
+               int lmax_out, double *cl);
+
+/* ---- introspection --------------------------------------------------------- */
+/* device milliseconds of the stages of the last hcu_map2alm / hcu_alm2map call
+ * (CUDA events on the context stream): [0] ring FFT stage, [1] Legendre stage,
+ * [2] synthesis Legendre, [3] synthesis FFT.  Synchronises. */
+int hcu_last_sht_timing(hcu_ctx *ctx, float ms[4]);
+/* executed Legendre work of the last analysis call: number of (l, ring-pair)
+ * cells advanced by the recursion and the number that were accumulated */
+int hcu_last_sht_work(hcu_ctx *ctx, double *cells_recursed, double *cells_accumulated);
+/* peak FP64 FMA rate of this device measured with a register-resident DFMA
+ * loop (flop/s); used as the roofline denominator of the Legendre stage */
+int hcu_measure_fp64_peak(hcu_ctx *ctx, double *flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HERACLES_CUDA_H */

@@ -1,0 +1,262 @@
+"""
+map -> alm parity on the GPU against the CPU oracle (through the C ABI).
+Tolerance: north_star's 1e-10 relative for alm in FP64, measured as
+||da||_2 / ||a||_2 per component and max |da_lm| / sqrt(max C_l).
+"""
+import numpy as np
+import numpy.testing as npt
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def random_maps(nside, k, seed):
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((k, 12 * nside * nside))
+
+
+def gpu_phase(ctx, nside, lmax, maps, rp_lo=0, rp_hi=None):
+    """hcu_map2phase on device copies; returns phase[m, rp, c, 4]"""
+    from heracles_b200 import DeviceArray, _lib
+
+    nrp = 2 * nside
+    rp_hi = nrp if rp_hi is None else rp_hi
+    k = maps.shape[0]
+    dm = DeviceArray.zeros(ctx, maps.shape)
+    dm[:] = maps
+    dm.to_device()
+    ph = DeviceArray.zeros(ctx, (lmax + 1, rp_hi - rp_lo, k, 4))
+    _lib.check(
+        ctx.lib.hcu_map2phase(ctx.handle, nside, lmax, k, dm.device_ptr, maps.shape[1], None, rp_lo, rp_hi, ph.device_ptr)
+    )
+    ctx.synchronize()
+    return np.array(ph._host(), copy=True)
+
+
+@pytest.mark.parametrize("nside,lmax", [(1, 2), (2, 7), (4, 8), (8, 32), (16, 24), (64, 128), (32, 128)])
+def test_ring_fft_stage(ctx, oracle, nside, lmax):
+    maps = random_maps(nside, 3, nside)
+    ph = gpu_phase(ctx, nside, lmax, maps)
+    ref = oracle.map2phase(nside, lmax, maps)  # [c, ring, m]
+    nr = 4 * nside - 1
+    scale = np.abs(ref).max()
+    for rp in range(2 * nside):
+        n = ref[:, rp, :]
+        s = ref[:, nr - 1 - rp, :] if nr - 1 - rp != rp else np.zeros_like(n)
+        plus = ph[:, rp, :, 0] + 1j * ph[:, rp, :, 1]
+        minus = ph[:, rp, :, 2] + 1j * ph[:, rp, :, 3]
+        npt.assert_allclose(plus.T, n + s, rtol=0, atol=1e-12 * scale, err_msg=f"ring pair {rp} (+)")
+        npt.assert_allclose(minus.T, n - s, rtol=0, atol=1e-12 * scale, err_msg=f"ring pair {rp} (-)")
+
+
+def test_ring_fft_stage_subrange(ctx, oracle):
+    nside, lmax = 16, 40
+    maps = random_maps(nside, 2, 7)
+    full = gpu_phase(ctx, nside, lmax, maps)
+    part = gpu_phase(ctx, nside, lmax, maps, 5, 23)
+    npt.assert_array_equal(part, full[:, 5:23])
+
+
+@pytest.mark.parametrize("spin", [0, 2])
+def test_golden_direct_sum(hb, spin):
+    g = golden("sht_direct_nside4.npz")
+    mapper = hb.CudaHealpixMapper(4, 8, deconvolve=False, niter=0)
+    if spin == 0:
+        alm = np.asarray(mapper.transform(g["T"], spin=0))
+        assert np.abs(alm - g["aT"]).max() < 1e-13
+    else:
+        alm = np.asarray(mapper.transform(np.stack([g["Q"], g["U"]]), spin=2))
+        assert np.abs(alm[0] - g["aE"]).max() < 1e-13
+        assert np.abs(alm[1] - g["aB"]).max() < 1e-13
+
+
+@pytest.mark.parametrize(
+    "nside,lmax,k",
+    [(1, 2, 1), (2, 4, 2), (8, 16, 1), (16, 48, 3), (32, 64, 10), (64, 96, 11), (128, 256, 2), (256, 512, 4)],
+)
+def test_map2alm_spin0(hb, oracle, nside, lmax, k):
+    maps = random_maps(nside, k, 100 + nside)
+    mapper = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=0)
+    alm = np.asarray(mapper.transform(maps, spin=0))
+    ref = oracle.map2alm(nside, lmax, maps, spin=0)
+    assert alm.shape == ref.shape == (k, (lmax + 1) * (lmax + 2) // 2)
+    for c in range(k):
+        assert relerr(alm[c], ref[c]) < TOL
+    assert np.abs(alm - ref).max() < TOL * np.abs(ref).max() * 10
+    # a_l0 is real
+    assert np.abs(alm[:, : lmax + 1].imag).max() == 0.0
+
+
+@pytest.mark.parametrize("nside,lmax,nf", [(2, 4, 1), (8, 16, 1), (16, 48, 2), (32, 64, 5), (64, 128, 6), (256, 512, 1)])
+def test_map2alm_spin2(hb, oracle, nside, lmax, nf):
+    maps = random_maps(nside, 2 * nf, 200 + nside).reshape(nf, 2, -1)
+    mapper = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=0)
+    alm = np.asarray(mapper.transform(maps, spin=2))
+    ref = oracle.map2alm(nside, lmax, maps.reshape(2 * nf, -1), spin=2).reshape(nf, 2, -1)
+    assert alm.shape == ref.shape
+    for f in range(nf):
+        for c in range(2):
+            assert relerr(alm[f, c], ref[f, c]) < TOL, (f, c)
+    # l < 2 modes vanish
+    for l in (0, 1):
+        for m in range(l + 1):
+            assert np.all(alm[..., m * (2 * lmax + 1 - m) // 2 + l] == 0)
+
+
+def test_single_map_shapes_and_metadata(hb):
+    # tests/test_healpy.py:81-116 (there with healpy.map2alm mocked)
+    nside = 32
+    npix = 12 * nside**2
+    mapper = hb.CudaHealpixMapper(nside, deconvolve=False)
+    rng = np.random.default_rng(50)
+    m = rng.standard_normal(npix)
+    hb.update_metadata(m, spin=0, nside=nside, a=1)
+    alms = mapper.transform(m, spin=0)
+    assert alms.shape == ((mapper.lmax + 1) * (mapper.lmax + 2) // 2,)
+    assert alms.dtype == np.complex128
+    assert alms.dtype.metadata["spin"] == 0
+    assert alms.dtype.metadata["a"] == 1
+    assert alms.dtype.metadata["nside"] == nside
+    assert alms.dtype.metadata["deconv"] is False
+    m = rng.standard_normal((2, npix))
+    hb.update_metadata(m, spin=2, nside=nside, b=2)
+    alms = mapper.transform(m, spin=2)
+    assert alms.shape == (2, (mapper.lmax + 1) * (mapper.lmax + 2) // 2)
+    assert alms.dtype.metadata["spin"] == 2
+    assert alms.dtype.metadata["b"] == 2
+    with pytest.raises(NotImplementedError):
+        mapper.transform(m, spin=1)
+
+
+def test_deconvolve(hb, oracle):
+    # tests/test_healpy.py:119-163: alm[l, m] scales by 1/pw[l] for l >= |spin|
+    nside, lmax = 32, 48
+    rng = np.random.default_rng(5)
+    pw0 = 1.0 / (1.0 + 0.01 * np.arange(lmax + 1))
+    pw2 = 1.0 / (1.0 + 0.02 * np.arange(lmax + 1))
+    pw2[:2] = 123.0  # must not be used
+    maps = rng.standard_normal((2, 12 * nside**2))
+    plain = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=0)
+    decon = hb.CudaHealpixMapper(nside, lmax, deconvolve=True, niter=0, pixwin=(pw0, pw2))
+    for spin, pw in ((0, pw0), (2, pw2)):
+        a = np.asarray(plain.transform(maps, spin=spin))
+        b = decon.transform(maps, spin=spin)
+        assert b.dtype.metadata["deconv"] is True
+        fl = np.ones(lmax + 1)
+        fl[spin:] /= pw[spin:]
+        npt.assert_allclose(np.asarray(b), oracle.almxfl(a, fl), rtol=1e-14, atol=0)
+    # niter > 0 applies the window once, at the end
+    d3 = hb.CudaHealpixMapper(nside, lmax, deconvolve=True, niter=2, pixwin=(pw0, pw2))
+    p3 = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=2)
+    fl = 1 / pw0
+    npt.assert_allclose(
+        np.asarray(d3.transform(maps[0], spin=0)), oracle.almxfl(np.asarray(p3.transform(maps[0], spin=0)), fl), rtol=1e-13
+    )
+
+
+@pytest.mark.parametrize("spin", [0, 2])
+@pytest.mark.parametrize("nside,lmax", [(8, 16), (32, 48), (64, 128)])
+def test_alm2map(hb, ctx, oracle, spin, nside, lmax):
+    from heracles_b200 import _lib
+
+    rng = np.random.default_rng(nside + spin)
+    na = (lmax + 1) * (lmax + 2) // 2
+    alm = rng.standard_normal((2, na)) + 1j * rng.standard_normal((2, na))
+    alm[:, : lmax + 1] = alm[:, : lmax + 1].real
+    if spin == 2:
+        for l in (0, 1):
+            for m in range(l + 1):
+                alm[:, m * (2 * lmax + 1 - m) // 2 + l] = 0
+    maps = np.empty((2, 12 * nside**2))
+    _lib.check(
+        ctx.lib.hcu_alm2map(ctx.handle, nside, lmax, spin, 2, alm.ctypes.data, na, maps.ctypes.data, maps.shape[1])
+    )
+    ref = oracle.alm2map(nside, lmax, alm, spin=spin)
+    assert relerr(maps, ref) < TOL
+
+
+@pytest.mark.parametrize("spin", [0, 2])
+def test_map2alm_iterated(hb, oracle, spin):
+    nside, lmax = 32, 64
+    maps = random_maps(nside, 2, 9)
+    mapper = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=3)
+    alm = np.asarray(mapper.transform(maps, spin=spin))
+    ref = oracle.map2alm(nside, lmax, maps, spin=spin, niter=3)
+    for c in range(2):
+        assert relerr(alm[c], ref[c]) < TOL
+
+
+def test_band_limited_round_trip(hb, oracle):
+    # size-independent property: analysis(synthesis(alm)) -> alm for lmax <= nside with iterations
+    nside, lmax = 64, 64
+    rng = np.random.default_rng(2)
+    na = (lmax + 1) * (lmax + 2) // 2
+    alm = rng.standard_normal(na) + 1j * rng.standard_normal(na)
+    alm[: lmax + 1] = alm[: lmax + 1].real
+    m = oracle.alm2map(nside, lmax, alm[None], spin=0)[0]
+    mapper = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=3)
+    back = np.asarray(mapper.transform(m, spin=0))
+    assert relerr(back, alm) < 1e-7
+
+
+def test_linearity_regions(hb):
+    # tests/test_dices.py:30-55: sum of region alms == alm of the full map
+    nside, lmax = 64, 96
+    rng = np.random.default_rng(4)
+    m = rng.standard_normal(12 * nside**2)
+    region = rng.integers(0, 3, m.size)
+    mapper = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=0)
+    full = np.asarray(mapper.transform(m, spin=0))
+    parts = sum(np.asarray(mapper.transform(np.where(region == r, m, 0.0), spin=0)) for r in range(3))
+    assert relerr(parts, full) < 1e-12
+
+
+def test_pixel_weights(hb, oracle):
+    nside, lmax = 16, 32
+    rng = np.random.default_rng(6)
+    m = rng.standard_normal((2, 12 * nside**2))
+    pw = 1.0 + 0.01 * rng.standard_normal(m.shape[1])
+    mapper = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=1, pixel_weights=pw)
+    alm = np.asarray(mapper.transform(m, spin=0))
+    ref = oracle.map2alm(nside, lmax, m, spin=0, niter=1, pixel_weights=pw)
+    assert relerr(alm, ref) < TOL
+
+
+def test_sparse_map_large_nside(hb, oracle):
+    # exact closed form at any nside: K non-zero pixels => a_lm = sum_k w v_k conj(Y_lm(theta_k, phi_k))
+    from scipy.special import sph_harm_y
+
+    nside, lmax = 1024, 2048
+    npix = 12 * nside**2
+    rng = np.random.default_rng(8)
+    ipix = np.array([0, 5, 1234567, npix // 2 + 3, npix - 1, 7 * nside * nside])
+    vals = rng.standard_normal(ipix.size)
+    m = np.zeros(npix)
+    m[ipix] = vals
+    lon, lat = oracle.pix2ang(nside, ipix)
+    # use exact ring geometry for theta
+    theta = np.radians(90.0 - lat)
+    phi = np.radians(lon)
+    mapper = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=0)
+    alm = np.asarray(mapper.transform(m, spin=0))
+    w = 4 * np.pi / npix
+    for l, mm in [(0, 0), (2, 1), (100, 37), (1500, 1499), (2048, 0), (2048, 2048), (2047, 1000), (777, 5)]:
+        if l <= 100:
+            ylm = sph_harm_y(l, mm, theta, phi)
+        else:  # scipy overflows at large l: use the oracle's long-double lambda_lm
+            lam = np.array(
+                [oracle.lambda_lm(lmax, mm, 0, np.cos(t), np.sin(t), prec=1)[l] for t in theta]
+            )
+            ylm = lam * np.exp(1j * mm * phi)
+        exp = w * np.sum(vals * np.conj(ylm))
+        got = alm[mm * (2 * lmax + 1 - mm) // 2 + l]
+        assert abs(got - exp) < 1e-9 * w * np.abs(vals).sum(), (l, mm, got, exp)

@@ -1,0 +1,144 @@
+"""
+CPU tests: the oracle against the committed golden fixtures and independent
+closed forms (no GPU needed).
+"""
+import numpy as np
+import numpy.testing as npt
+import pytest
+
+from conftest import golden
+
+
+def test_ang2pix_golden_cases(oracle):
+    g = golden("ang2pix_cases.npz")
+    for ns, lo, la, p in zip(g["nside"], g["lon"], g["lat"], g["ring"]):
+        assert oracle.ang2pix(int(ns), np.array([lo]), np.array([la]))[0] == p
+
+
+@pytest.mark.parametrize("nside", [1, 2, 8, 64, 1024])
+def test_pixel_round_trips(oracle, nside):
+    npix = 12 * nside * nside
+    ip = np.arange(npix) if npix < 200_000 else np.random.default_rng(1).integers(0, npix, 100_000)
+    lon, lat = oracle.pix2ang(nside, ip)
+    npt.assert_array_equal(oracle.ang2pix(nside, lon, lat), ip)
+    npt.assert_array_equal(oracle.ang2pix(nside, lon, lat, nest=True), oracle.ring2nest(nside, ip))
+    npt.assert_array_equal(oracle.nest2ring(nside, oracle.ring2nest(nside, ip)), ip)
+    lon_n, lat_n = oracle.pix2ang(nside, ip, nest=True)
+    npt.assert_array_equal(oracle.ang2pix(nside, lon_n, lat_n, nest=True), ip)
+
+
+def test_ang2pix_rejects_bad_latitude(oracle):
+    with pytest.raises(ValueError):
+        oracle.ang2pix(4, np.array([0.0]), np.array([90.1]))
+
+
+def test_equal_area_pixels(oracle):
+    # a dense uniform sample fills every pixel about equally
+    nside = 4
+    rng = np.random.default_rng(0)
+    n = 2_000_000
+    lon = rng.uniform(0, 360, n)
+    lat = np.degrees(np.arcsin(rng.uniform(-1, 1, n)))
+    counts = np.bincount(oracle.ang2pix(nside, lon, lat), minlength=12 * nside * nside)
+    assert abs(counts / counts.mean() - 1).max() < 0.05
+
+
+def test_map_values_is_sequential_scatter(oracle, rng):
+    nside = 16
+    n = 5000
+    lon = rng.uniform(0, 360, n)
+    lat = np.degrees(np.arcsin(rng.uniform(-1, 1, n)))
+    v = rng.standard_normal((2, n))
+    m = np.zeros((2, 12 * nside * nside))
+    oracle.map_values(nside, lon, lat, m, v)
+    exp = np.zeros_like(m)
+    ipix = oracle.ang2pix(nside, lon, lat)
+    np.add.at(exp[0], ipix, v[0])
+    np.add.at(exp[1], ipix, v[1])
+    npt.assert_array_equal(m, exp)
+
+
+def test_alm2cl_reference_golden(oracle):
+    g = golden("alm2cl_reference.npz")
+    cases = dict(
+        cl_pos_pos=("pos", "pos", {}),
+        cl_pos_pos2=("pos", "pos2", {}),
+        cl_pos_she=("pos", "she", {}),
+        cl_she_she=("she", "she", {}),
+        cl_she_she2=("she", "she2", {}),
+        cl_pos_pos_lmax20=("pos", "pos2", dict(lmax=20)),
+        cl_u=("ua", "ub", {}),
+        cl_u_lmax20=("ua", "ub", dict(lmax=20)),
+    )
+    for key, (a, b, kw) in cases.items():
+        cl = oracle.alm2cl(g[a], g[b], **kw)
+        assert cl.shape == g[key].shape
+        npt.assert_array_equal(cl, g[key])  # bit-exact: same running-mean update
+
+
+def test_alm2lmax(oracle):
+    for lmax in (0, 1, 5, 32, 999):
+        assert oracle.alm2lmax(np.zeros((lmax + 1) * (lmax + 2) // 2)) == lmax
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_sht_direct_sum_golden(oracle, prec):
+    g = golden("sht_direct_nside4.npz")
+    a = oracle.map2alm(4, 8, g["T"], prec=prec)
+    assert np.abs(a - g["aT"]).max() < 5e-15
+    a = oracle.map2alm(4, 8, np.stack([g["Q"], g["U"]]), spin=2, prec=prec)
+    assert np.abs(a[0] - g["aE"]).max() < 5e-15
+    assert np.abs(a[1] - g["aB"]).max() < 5e-15
+
+
+def test_lambda_against_scipy(oracle):
+    from scipy.special import sph_harm_y
+
+    lmax = 40
+    for c in (0.3, -0.7, 0.999):
+        s = np.sqrt(1 - c * c)
+        for m in (0, 1, 7, 40):
+            lam = oracle.lambda_lm(lmax, m, 0, c, s)
+            ref = np.array([sph_harm_y(l, m, np.arccos(c), 0.0).real if l >= m else 0 for l in range(lmax + 1)])
+            assert np.abs(lam - ref).max() < 1e-11  # sqrt(1-c^2) in double limits the inputs
+
+
+def test_double_vs_long_double(oracle):
+    nside, lmax = 32, 64
+    rng = np.random.default_rng(3)
+    m = rng.standard_normal((2, 12 * nside * nside))
+    for spin in (0, 2):
+        a = oracle.map2alm(nside, lmax, m, spin=spin)
+        b = oracle.map2alm(nside, lmax, m, spin=spin, prec=1)
+        assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-13
+
+
+@pytest.mark.parametrize("spin", [0, 2])
+def test_round_trip_with_iterations(oracle, spin):
+    nside, lmax = 16, 16
+    rng = np.random.default_rng(4)
+    na = (lmax + 1) * (lmax + 2) // 2
+    a = rng.standard_normal((2, na)) + 1j * rng.standard_normal((2, na))
+    a[:, : lmax + 1] = a[:, : lmax + 1].real
+    if spin == 2:
+        for l in (0, 1):
+            for mm in range(l + 1):
+                a[:, oracle.almidx(lmax, l, mm)] = 0
+    m = oracle.alm2map(nside, lmax, a, spin=spin)
+    b0 = oracle.map2alm(nside, lmax, m, spin=spin, niter=0)
+    b3 = oracle.map2alm(nside, lmax, m, spin=spin, niter=3)
+    e0 = np.abs(b0 - a).max()
+    e3 = np.abs(b3 - a).max()
+    assert e3 < 1e-6 and e3 < e0 * 1e-2
+
+
+def test_scaled_recursion_large_m(oracle):
+    # sin^m(theta) far below the double range must not break the recursion
+    lmax = 3000
+    lam = oracle.lambda_lm(lmax, 2500, 0, 0.2, np.sqrt(1 - 0.04))
+    lam_ld = oracle.lambda_lm(lmax, 2500, 0, 0.2, np.sqrt(1 - 0.04), prec=1)
+    assert np.all(np.isfinite(lam))
+    assert abs(lam[lmax]) > 1e-3
+    assert np.abs(lam - lam_ld).max() < 1e-12
+    tiny = oracle.lambda_lm(lmax, 2500, 0, 0.9999, np.sqrt(1 - 0.9999**2))
+    assert np.all(tiny == 0.0)
