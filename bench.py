@@ -1,0 +1,584 @@
+#!/usr/bin/env python
+"""
+bench.py -- catalogue -> HEALPix maps -> alm -> Cl, seconds per run.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C1|C2|C3|C4|auto]
+                    [--niter I] [--impl b200|reference]
+
+A "step" is one complete pass of the hot path over the whole synthetic
+catalogue of the chosen BASELINE.json configuration: every page of every
+tomographic bin is mapped (POS: weights; SHE: w*g1, w*g2), the maps are
+normalised as the reference's Field layer does (heracles/fields.py:296-304,446),
+all maps are transformed (spin 0 and spin 2) and every component cross spectrum
+is computed.  Prints ONE JSON line (rank 0).
+
+  value       device-resident arm: catalogue pages already in HBM, C ABI called
+              with device pointers.
+  e2e         the same pass through the public plugin API
+              (CudaHealpixMapper.map_values / heracles_b200.transform /
+              angular_power_spectra) with pinned HOST pages; H2D of every page
+              and D2H of the spectra are inside the timed region.
+  roofline    the dominant kernel (FP64 Legendre analysis): executed flops /
+              CUDA-event time against the DFMA peak measured in the same run.
+  cpu_baseline  the oracle (CPU restatement of the reference path) timed on a
+              bounded sample and scaled to the full configuration.
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: nside, lmax, bins, rows per bin, fields
+    "C1": dict(nside=256, lmax=512, nbins=1, rows=1_000_000, she=False,
+               text="nside=256 lmax=512 spin-0 Positions map from 1e6-galaxy synthetic uniform catalogue"),
+    "C2": dict(nside=1024, lmax=2048, nbins=1, rows=100_000_000, she=True,
+               text="nside=1024 lmax=2048 POS+SHE from 1e8 galaxies, single field pair"),
+    "C3": dict(nside=2048, lmax=4096, nbins=5, rows=100_000_000, she=True,
+               text="nside=2048 lmax=4096 5 tomographic bins x POS+SHE, all cross-spectra"),
+    "C4": dict(nside=4096, lmax=8192, nbins=10, rows=200_000_000, she=True,
+               text="nside=4096 lmax=8192 10 tomographic bins x POS+SHE from 2e9 synthetic galaxies"),
+}
+PAGE_ROWS = 1_000_000  # heracles/catalog/base.py:315
+POOL_PAGES = 64        # distinct pages per bin, cycled to reach the row count
+METRIC = "catalog_to_cl_seconds_per_run"
+UNIT = "s/run"
+
+
+# ---------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(smax)) if smax else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def pick_config(name, free_bytes):
+    if name != "auto":
+        return name
+    return "C4" if free_bytes > 150e9 else ("C3" if free_bytes > 40e9 else "C2")
+
+
+def legendre_flops(spin, ncomp, rec, acc):
+    """executed flops from the kernels' work counters (SURVEY 8(d) per-cell figures)"""
+    if spin == 0:
+        return rec * 4.0 + acc * 4.0 * ncomp
+    return rec * 12.0 + acc * 16.0 * (ncomp // 2)
+
+
+def nominal_sht_flops(cfg, niter):
+    nalm = (cfg["lmax"] + 1) * (cfg["lmax"] + 2) // 2
+    n0 = cfg["nbins"]
+    n2 = cfg["nbins"] if cfg["she"] else 0
+    per_pass = nalm * (2 * cfg["nside"]) * ((4 + 4 * n0) + ((12 + 16 * n2) if n2 else 0))
+    return per_pass * (1 + 2 * niter)
+
+
+# ---------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------
+class Pipeline:
+    def __init__(self, cfg, niter, rank, world, torch, hb):
+        self.cfg, self.niter, self.rank, self.world = cfg, niter, rank, world
+        self.torch, self.hb = torch, hb
+        self.ctx = hb.get_context(torch.cuda.current_device())
+        self.lib = self.ctx.lib
+        self.h = self.ctx.handle
+        self.stream = torch.cuda.Stream()
+        self.ctx.set_stream(self.stream.cuda_stream)
+        nside, lmax = cfg["nside"], cfg["lmax"]
+        self.npix = 12 * nside * nside
+        self.nalm = (lmax + 1) * (lmax + 2) // 2
+        self.nbins = cfg["nbins"]
+        self.ncomp = self.nbins * (3 if cfg["she"] else 1)
+        self.pages = max(1, cfg["rows"] // PAGE_ROWS)
+        self.page_rows = min(PAGE_ROWS, cfg["rows"])
+        self.pool = min(POOL_PAGES, self.pages)
+        self.make_catalogue()
+
+    # synthetic catalogue: uniform positions, w ~ U(0.5,1.5), g ~ N(0,0.3)  
+    def make_catalogue(self):
+        torch = self.torch
+        dev = torch.device("cuda")
+        n = self.pool * self.page_rows
+        self.cat = []
+        self.norm = []
+        for b in range(self.nbins):
+            g = torch.Generator(device=dev)
+            g.manual_seed(50 + 1000 * b)
+            lon = torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 360.0
+            lat = torch.rad2deg(torch.asin(torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 2 - 1))
+            w = torch.rand(n, generator=g, device=dev, dtype=torch.float64) + 0.5
+            cols = {"lon": lon, "lat": lat, "w": w}
+            if self.cfg["she"]:
+                # per page a contiguous (2, rows) block like np.r_[[re, im]] (fields.py:428)
+                gg = torch.randn(self.pool, 2, self.page_rows, generator=g, device=dev, dtype=torch.float64) * 0.3
+                gg *= w.view(self.pool, 1, self.page_rows)
+                cols["wg"] = gg.contiguous()
+            self.cat.append(cols)
+            # the Field layer's running means over the whole (cycled) catalogue
+            reps = np.bincount(np.arange(self.pages) % self.pool, minlength=self.pool).astype(np.float64)
+            wp = w.view(self.pool, self.page_rows).sum(dim=1).cpu().numpy()
+            ngal = self.pages * self.page_rows
+            wmean = float((wp * reps).sum() / ngal)
+            nbar = ngal * wmean / self.npix                      # fields.py:283 (fsky = 1)
+            wbar = ngal / (4 * math.pi) * wmean * (4 * math.pi / self.npix)  # fields.py:440
+            self.norm.append((nbar, wbar))
+        torch.cuda.synchronize()
+
+    def my_pages(self):
+        """catalogue rows are sharded across ranks page by page"""
+        return range(self.rank, self.pages, self.world)
+
+    def alloc_outputs(self):
+        torch = self.torch
+        dev = torch.device("cuda")
+        self.maps = torch.empty(self.ncomp, self.npix, device=dev, dtype=torch.float64)
+        self.alm = torch.empty(self.ncomp, self.nalm, device=dev, dtype=torch.complex128)
+        self.cl = torch.empty(self.ncomp, self.ncomp, self.cfg["lmax"] + 1, device=dev, dtype=torch.float64)
+
+    # ---- stages (device-resident) ----
+    def stage_map(self):
+        lib, h, npix, nside = self.lib, self.h, self.npix, self.cfg["nside"]
+        self.maps.zero_()
+        rows = self.page_rows
+        for b in range(self.nbins):
+            c = self.cat[b]
+            pos_ptr = self.maps[b].data_ptr()
+            she_ptr = self.maps[self.nbins + 2 * b].data_ptr() if self.cfg["she"] else 0
+            lon0, lat0, w0 = c["lon"].data_ptr(), c["lat"].data_ptr(), c["w"].data_ptr()
+            wg0 = c["wg"].data_ptr() if self.cfg["she"] else 0
+            for p in self.my_pages():
+                off = (p % self.pool) * rows * 8
+                self.check(lib.hcu_map_values(h, nside, 0, lon0 + off, lat0 + off, w0 + off, rows, 1, rows, pos_ptr, npix, 0))
+                if self.cfg["she"]:
+                    self.check(lib.hcu_map_values(h, nside, 0, lon0 + off, lat0 + off, wg0 + 2 * off, rows, 2, rows, she_ptr, npix, 0))
+
+    def stage_normalise(self):
+        lib, h, npix = self.lib, self.h, self.npix
+        for b in range(self.nbins):
+            nbar, wbar = self.norm[b]
+            p = self.maps[b].data_ptr()
+            self.check(lib.hcu_divide(h, p, npix, nbar))          # pos /= nbar
+            self.check(lib.hcu_add_scalar(h, p, npix, -1.0))      # pos -= vis (full sky)
+            if self.cfg["she"]:
+                self.check(lib.hcu_divide(h, self.maps[self.nbins + 2 * b].data_ptr(), 2 * npix, wbar))
+
+    def stage_transform(self, stats):
+        lib, h, cfg = self.lib, self.h, self.cfg
+        nb = self.nbins
+        calls = [(0, 0, nb)]
+        if cfg["she"]:
+            calls.append((2, nb, 2 * nb))
+        for spin, row0, n in calls:
+            self.check(lib.hcu_map2alm(h, cfg["nside"], cfg["lmax"], spin, n, self.maps[row0].data_ptr(), self.npix,
+                                       None, None, self.niter, None, self.alm[row0].data_ptr(), self.nalm))
+            ms = self.ctx.sht_timing()
+            rec, acc = self.ctx.sht_work()
+            stats["fft_ms"] += ms[0] + ms[3]
+            stats["leg_ana_ms"] += ms[1]
+            stats["leg_syn_ms"] += ms[2]
+            # counters cover every analysis pass of the call; batches of <= 10 components
+            stats["leg_ana_flops"] += legendre_flops(spin, min(n, 10), rec, acc)
+
+    def stage_cl(self):
+        cfg = self.cfg
+        self.check(self.lib.hcu_alm2cl(self.h, self.ncomp, self.alm.data_ptr(), self.nalm, cfg["lmax"], self.ncomp,
+                                       self.alm.data_ptr(), self.nalm, cfg["lmax"], cfg["lmax"], self.cl.data_ptr()))
+
+    def check(self, status):
+        if status != 0:
+            from heracles_b200 import _lib
+            _lib.check(status)
+
+    def step(self, stats):
+        torch = self.torch
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        with torch.cuda.stream(self.stream):
+            ev[0].record()
+            self.stage_map()
+            ev[1].record()
+            self.stage_normalise()
+            if self.world > 1:
+                self.reduce_maps()
+            ev[2].record()
+            self.stage_transform(stats)
+            ev[3].record()
+            self.stage_cl()
+            ev[4].record()
+        ev[4].synchronize()
+        stats["map_ms"] += ev[0].elapsed_time(ev[1])
+        stats["norm_ms"] += ev[1].elapsed_time(ev[2])
+        stats["sht_ms"] += ev[2].elapsed_time(ev[3])
+        stats["cl_ms"] += ev[3].elapsed_time(ev[4])
+        return ev[0].elapsed_time(ev[4])
+
+    def reduce_maps(self):
+        import torch.distributed as dist
+        self.stream.synchronize()
+        dist.all_reduce(self.maps)
+        self.torch.cuda.synchronize()
+
+    # ---- end-to-end through the public API with pinned host pages ----
+    def make_host_pool(self):
+        torch = self.torch
+        self.hcat = []
+        for b in range(self.nbins):
+            c = self.cat[b]
+            hc = {}
+            for k, v in c.items():
+                t = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                t.copy_(v)
+                hc[k] = t.numpy()
+            self.hcat.append(hc)
+        torch.cuda.synchronize()
+
+    def e2e_step(self):
+        hb = self.hb
+        cfg, rows = self.cfg, self.page_rows
+
+        class F:  # the two attributes heracles.mapping.transform reads from a Field
+            def __init__(self, mapper, spin):
+                self.mapper_or_error, self.spin = mapper, spin
+
+        mapper = hb.CudaHealpixMapper(cfg["nside"], cfg["lmax"], deconvolve=False, niter=self.niter, sync=False)
+        fields = {"POS": F(mapper, 0), "SHE": F(mapper, 2)}
+        t0 = time.perf_counter()
+        maps = {}
+        h2d = 0
+        vis = mapper.create()
+        vis += 1.0
+        for b in range(self.nbins):
+            hc = self.hcat[b]
+            pos = mapper.create(spin=0)
+            she = mapper.create(2, spin=2) if cfg["she"] else None
+            for p in self.my_pages():
+                s = (p % self.pool) * rows
+                lon, lat, w = hc["lon"][s:s + rows], hc["lat"][s:s + rows], hc["w"][s:s + rows]
+                mapper.map_values(lon, lat, pos, w, spin=0)
+                h2d += 3 * rows * 8
+                if she is not None:
+                    mapper.map_values(lon, lat, she, hc["wg"][p % self.pool], spin=2)
+                    h2d += 4 * rows * 8
+            nbar, wbar = self.norm[b]
+            pos /= nbar
+            pos -= vis
+            maps["POS", b] = pos
+            if she is not None:
+                she /= wbar
+                maps["SHE", b] = she
+        bad = mapper.context.bad_rows()
+        assert bad == 0
+        alms = hb.transform(fields, maps)
+        for (k, i), a in alms.items():
+            hb.update_metadata(a, spin=0 if k == "POS" else 2)
+        cls = hb.angular_power_spectra(alms, debias=False)
+        d2h = sum(np.asarray(c).nbytes for c in cls.values())
+        checksum = float(sum(np.asarray(c).sum() for c in cls.values()))
+        dt = time.perf_counter() - t0
+        return dt, h2d, d2h, checksum, len(cls)
+
+
+def cpu_sample(cfg, niter, threads=None):
+    """
+    Time the oracle (CPU restatement of the reference path) on a bounded sample
+    of the configuration and scale to one full run.  Returns (seconds_per_run, info).
+    """
+    import oracle
+
+    oracle.build()
+    if threads:
+        oracle.set_num_threads(threads)
+    cores = oracle.num_threads()
+    rng = np.random.default_rng(50)
+    # 1. catalogue -> map at the real nside, 1 thread like the reference (healpy.py:157-160)
+    n = 1_000_000
+    lon = rng.uniform(0, 360, n)
+    lat = np.degrees(np.arcsin(rng.uniform(-1, 1, n)))
+    w = rng.uniform(0.5, 1.5, n)
+    g = rng.normal(0, 0.3, (2, n)) * w
+    nside = cfg["nside"]
+    pos = np.zeros(12 * nside * nside)
+    t = time.perf_counter()
+    oracle.map_values(nside, lon, lat, pos, w)
+    t_pos = (time.perf_counter() - t) / n
+    t_she = 0.0
+    if cfg["she"]:
+        she = np.zeros((2, 12 * nside * nside))
+        t = time.perf_counter()
+        oracle.map_values(nside, lon, lat, she, g)
+        t_she = (time.perf_counter() - t) / n
+        del she
+    del pos
+    rows_total = cfg["rows"] * cfg["nbins"]
+    t_map = (t_pos + t_she) * rows_total
+    # 2. transforms at reduced resolution, all threads, same niter; cost ~ nside * lmax^2 per map
+    ns = min(nside, 256)
+    ls = 2 * ns
+    m = rng.standard_normal((2, 12 * ns * ns))
+    t = time.perf_counter()
+    oracle.map2alm(ns, ls, m[:1], spin=0, niter=niter)
+    t0 = time.perf_counter() - t
+    scale = (nside / ns) * (cfg["lmax"] / ls) ** 2
+    t_sht = t0 * scale * cfg["nbins"]
+    if cfg["she"]:
+        t = time.perf_counter()
+        oracle.map2alm(ns, ls, m, spin=2, niter=niter)
+        t_sht += (time.perf_counter() - t) * scale * cfg["nbins"]
+    # 3. alm2cl, the reference's running-mean loop, one thread
+    na = (ls + 1) * (ls + 2) // 2
+    a = rng.standard_normal(na) + 1j * rng.standard_normal(na)
+    t = time.perf_counter()
+    for _ in range(3):
+        oracle.alm2cl(a, a)
+    t_cl1 = (time.perf_counter() - t) / 3
+    ncomp = cfg["nbins"] * (3 if cfg["she"] else 1)
+    nalm = (cfg["lmax"] + 1) * (cfg["lmax"] + 2) // 2
+    t_cl = t_cl1 * (nalm / na) * ncomp * (ncomp + 1) / 2
+    total = t_map + t_sht + t_cl
+    info = {
+        "value": total, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": (f"oracle (CPU restatement of the healpy/ducc path): ang2pix+scatter on {n} rows at nside={nside} "
+                   f"(1 thread, {t_pos * 1e9:.0f}+{t_she * 1e9:.0f} ns/row) x {rows_total:.3g} rows; map2alm spin0+spin2 "
+                   f"niter={niter} at nside={ns} lmax={ls} ({cores} threads) scaled by nside*lmax^2 x {cfg['nbins']} bins; "
+                   f"alm2cl at lmax={ls} scaled by nalm x {ncomp * (ncomp + 1) // 2} spectra; "
+                   f"extrapolated stage seconds map/sht/cl = {t_map:.1f}/{t_sht:.1f}/{t_cl:.1f}"),
+    }
+    return total, info
+
+
+def run_reference(args, cfg_name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CONFIGS[cfg_name]
+    times = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        t, info = cpu_sample(cfg, args.niter)
+        if i >= args.warmup:
+            times.append(t)
+    val = float(np.mean(times))
+    info["value"] = val
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{cfg_name}: {cfg['text']}", "niter": args.niter,
+                   "note": "healpy/ducc are not installable here: the CPU arm is the oracle port, bounded sample scaled to the full run"},
+        "cpu_baseline": info,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="auto")
+    ap.add_argument("--niter", type=int, default=3, help="map2alm Jacobi iterations (healpy default 3)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        name = args.config if args.config != "auto" else "C4"
+        run_reference(args, name)
+        return
+
+    import torch
+
+    import heracles_b200 as hb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    free, total_mem = torch.cuda.mem_get_info()
+    cfg_name = pick_config(args.config, free)
+    cfg = CONFIGS[cfg_name]
+
+    pipe = Pipeline(cfg, args.niter, rank, world, torch, hb)
+    pipe.alloc_outputs()
+    ctx = pipe.ctx
+    fp64_peak = ctx.fp64_peak()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    stats = dict.fromkeys(["map_ms", "norm_ms", "sht_ms", "cl_ms", "fft_ms", "leg_ana_ms", "leg_syn_ms", "leg_ana_flops"], 0.0)
+    for _ in range(args.warmup):
+        pipe.step(dict(stats))
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launch_count()
+    for k in stats:
+        stats[k] = 0.0
+    total_ms = 0.0
+    barrier()
+    for _ in range(args.steps):
+        total_ms += pipe.step(stats)
+    barrier()
+    clocks = sampler.stop()
+    l1 = ctx.launch_count()
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    checksum = float(pipe.cl.sum().item())
+
+    # roofline of the dominant kernel and of the HBM-bound scatter
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    leg_tflops = stats["leg_ana_flops"] / max(stats["leg_ana_ms"], 1e-9) * 1e3 / 1e12
+    rows_step = len(pipe.my_pages()) * pipe.page_rows * cfg["nbins"]
+    map_bytes = rows_step * (40 + (64 if cfg["she"] else 0))
+    map_gbs = map_bytes * args.steps / max(stats["map_ms"], 1e-9) * 1e3 / 1e9
+    roofline = {
+        "kernel": "legendre_analysis_kernel", "bound": "fp64_fma", "achieved": leg_tflops, "peak": fp64_peak / 1e12,
+        "unit": "TFLOP/s", "frac": leg_tflops / (fp64_peak / 1e12), "traffic": None,
+        "peak_source": "DFMA microkernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+        "share_of_step": stats["leg_ana_ms"] / total_ms,
+    }
+    roofline_map = {
+        "kernel": "map_values_kernel", "bound": "hbm", "achieved": map_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "frac": map_gbs / hbm_peak, "traffic": None,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+        "share_of_step": stats["map_ms"] / total_ms,
+    }
+
+    line = {
+        "metric": METRIC, "value": ms_per_step / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": f"{cfg_name}: {cfg['text']}", "nside": cfg["nside"], "lmax": cfg["lmax"],
+            "fields": cfg["nbins"] * (2 if cfg["she"] else 1), "rows": cfg["rows"] * cfg["nbins"], "niter": args.niter,
+            "spectra": pipe.ncomp * (pipe.ncomp + 1) // 2,
+            "pages": f"{pipe.pages} pages of {pipe.page_rows} rows per bin cycling a pool of {pipe.pool} distinct pages",
+            "l2": "inputs larger than L2 (catalogue and maps are GBs); no flush needed",
+        },
+        "stage_ms_per_step": {k: stats[k] / args.steps for k in ("map_ms", "norm_ms", "sht_ms", "cl_ms", "fft_ms", "leg_ana_ms", "leg_syn_ms")},
+        "sht_fp64_tflops_nominal": nominal_sht_flops(cfg, args.niter) / (stats["sht_ms"] / args.steps * 1e-3) / 1e12 if stats["sht_ms"] else None,
+        "roofline": roofline, "roofline_map_values": roofline_map,
+        "gpu_launches": int((l1[0] - l0[0]) + (l1[1] - l0[1])),
+        "gpu_launches_detail": {"own_kernels": int(l1[0] - l0[0]), "cufft_execs": int(l1[1] - l0[1])},
+        "clocks": clocks, "checksum": checksum,
+    }
+
+    # end to end through the plugin API, host pages
+    if not args.no_e2e:
+        pipe.make_host_pool()
+        del pipe.maps, pipe.alm, pipe.cl
+        torch.cuda.empty_cache()
+        ctx.trim()
+        res = None
+        pipe.e2e_step() if args.e2e_steps > 0 else None  # warm-up
+        barrier()
+        tt = 0.0
+        for _ in range(max(1, args.e2e_steps)):
+            res = pipe.e2e_step()
+            tt += res[0]
+        barrier()
+        if world > 1:
+            t = torch.tensor([tt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tt = float(t.item())
+        line["e2e"] = {"value": tt / max(1, args.e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(res[1]),
+                       "d2h_bytes_per_step": int(res[2]), "spectra": res[4], "checksum": res[3],
+                       "api": "CudaHealpixMapper.map_values(sync=False) + heracles_b200.transform + angular_power_spectra, pinned host pages"}
+
+    if rank == 0 and not args.no_cpu:
+        _, info = cpu_sample(cfg, args.niter)
+        line["cpu_baseline"] = info
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

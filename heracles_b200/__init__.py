@@ -17,6 +17,7 @@ context fails without a CUDA device.
 from ._lib import Context, HeraclesCudaError, get_context, load  # noqa: F401
 from .arrays import DeviceArray, update_metadata  # noqa: F401
 from .mapper import CudaHealpixMapper  # noqa: F401
+from .mapping import transform, transform_maps  # noqa: F401
 from .twopoint import alm2cl, alm2lmax, angular_power_spectra  # noqa: F401
 
 __all__ = [

@@ -48,6 +48,7 @@ SIGNATURES = {
     "hcu_add_scalar": (c_int, [c_vp, c_vp, c_i64, c_dbl]),
     "hcu_ud_grade": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp]),
     "hcu_map2alm": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_i64]),
+    "hcu_map2alm_many": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "hcu_alm2map": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_i64]),
     "hcu_map2phase": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "hcu_phase2alm": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_i64]),

@@ -183,6 +183,7 @@ static PtrKind ptr_kind(const void *p) {
   }
 }
 static bool dev_accessible(PtrKind k) { return k == PK_DEVICE || k == PK_MANAGED; }
+bool hcu_dev_accessible(const void *p) { return dev_accessible(ptr_kind(p)); }
 
 extern "C" int hcu_malloc_managed(hcu_ctx *ctx, size_t bytes, void **ptr) {
   HCU_ARG(ctx && ptr, "hcu_malloc_managed");
@@ -505,23 +506,6 @@ int hcu_get_coef(hcu_ctx *ctx, int lmax, int spin, hcu_coef **out) {
 // transforms
 // ---------------------------------------------------------------------------
 namespace {
-__global__ void almxfl_kernel(double2 *alm, i64 stride, int nrows, int lmax, const double *fl) {
-  const i64 nalm = (i64)(lmax + 1) * (lmax + 2) / 2;
-  const int m = blockIdx.x;
-  const i64 base = (i64)m * (2 * lmax + 1 - m) / 2;
-  (void)nalm;
-  for (int r = blockIdx.y; r < nrows; r += gridDim.y)
-    for (int l = m + threadIdx.x; l <= lmax; l += blockDim.x) {
-      double2 v = alm[(i64)r * stride + base + l];
-      const double f = fl[l];
-      alm[(i64)r * stride + base + l] = make_double2(v.x * f, v.y * f);
-    }
-}
-__global__ void sub_kernel(double *out, const double *a, const double *b, i64 n) {
-  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  i64 s = (i64)gridDim.x * blockDim.x;
-  for (; i < n; i += s) out[i] = a[i] - b[i];
-}
 __global__ void dfma_peak_kernel(double *out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
   double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -533,269 +517,6 @@ __global__ void dfma_peak_kernel(double *out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 }  // namespace
-
-static int upload_small(hcu_ctx *ctx, const double *src, size_t n, size_t slot_off, const double **dev) {
-  // small host arrays (fl, ring weights) go to ws_state; device arrays are used in place
-  if (!src) {
-    *dev = nullptr;
-    return HCU_OK;
-  }
-  if (dev_accessible(ptr_kind(src))) {
-    *dev = src;
-    return HCU_OK;
-  }
-  double *d = (double *)ctx->ws_state.ptr + slot_off;
-  HCU_CUDA(cudaMemcpyAsync(d, src, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-  HCU_CUDA(cudaStreamSynchronize(ctx->stream));
-  *dev = d;
-  return HCU_OK;
-}
-
-static int analysis_pass(hcu_ctx *ctx, hcu_geom *g, hcu_coef *cf, int lmax, int spin,
-                         int nmaps, const double *maps, i64 map_stride, const double *rw,
-                         const double *pw, const double *fl, double *alm, i64 alm_stride,
-                         float *ms_fft, float *ms_leg) {
-  const i64 nside = g->nside;
-  const i64 npix = 12 * nside * nside;
-  const i64 nrp = g->nrp;
-  const int cap = 10;
-  for (int c0 = 0; c0 < nmaps; c0 += cap) {
-    const int nb = std::min(cap, nmaps - c0);
-    const double *src = maps + (i64)c0 * map_stride;
-    i64 sstride = map_stride;
-    if (pw) {
-      HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_misc, sizeof(double) * npix * nb));
-      for (int c = 0; c < nb; ++c)
-        HCU_CHECK(hcu_mul(ctx, (double *)ctx->ws_misc.ptr + (i64)c * npix, src + (i64)c * map_stride, pw, npix));
-      src = (double *)ctx->ws_misc.ptr;
-      sstride = npix;
-    }
-    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_phase, sizeof(double) * 4 * (size_t)(lmax + 1) * nrp * nb));
-    double *phase = (double *)ctx->ws_phase.ptr;
-    HCU_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-    HCU_CHECK(hcu_ring_fft_forward(ctx, g, lmax, nb, src, sstride, rw, 0, nrp, phase));
-    HCU_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-    HCU_CHECK(hcu_legendre_analysis(ctx, g, cf, lmax, spin, nb, phase, nullptr, lmax + 1, 0, nrp,
-                                    fl, alm + 2 * (i64)c0 * alm_stride, alm_stride));
-    HCU_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-    HCU_CUDA(cudaEventSynchronize(ctx->ev[2]));
-    float t0 = 0, t1 = 0;
-    cudaEventElapsedTime(&t0, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]);
-    *ms_fft += t0;
-    *ms_leg += t1;
-  }
-  return HCU_OK;
-}
-
-static int synthesis_pass(hcu_ctx *ctx, hcu_geom *g, hcu_coef *cf, int lmax, int spin,
-                          int nmaps, const double *alm, i64 alm_stride, double *maps,
-                          i64 map_stride, float *ms_leg, float *ms_fft) {
-  const i64 nrp = g->nrp;
-  const int cap = 10;
-  for (int c0 = 0; c0 < nmaps; c0 += cap) {
-    const int nb = std::min(cap, nmaps - c0);
-    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_phase, sizeof(double) * 4 * (size_t)(lmax + 1) * nrp * nb));
-    double *phase = (double *)ctx->ws_phase.ptr;
-    HCU_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
-    HCU_CHECK(hcu_legendre_synthesis(ctx, g, cf, lmax, spin, nb, alm + 2 * (i64)c0 * alm_stride,
-                                     alm_stride, phase));
-    HCU_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
-    HCU_CHECK(hcu_ring_fft_inverse(ctx, g, lmax, nb, phase, maps + (i64)c0 * map_stride, map_stride));
-    HCU_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
-    HCU_CUDA(cudaEventSynchronize(ctx->ev[5]));
-    float t0 = 0, t1 = 0;
-    cudaEventElapsedTime(&t0, ctx->ev[3], ctx->ev[4]);
-    cudaEventElapsedTime(&t1, ctx->ev[4], ctx->ev[5]);
-    *ms_leg += t0;
-    *ms_fft += t1;
-  }
-  return HCU_OK;
-}
-
-static int check_sht_args(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps) {
-  HCU_ARG(ctx, "ctx");
-  HCU_ARG(valid_nside(nside) && nside <= 4096,
-          "nside must be a power of two <= 4096 (polar-cap FFT tile limit)");
-  HCU_ARG(lmax >= 0 && lmax <= 4 * nside, "0 <= lmax <= 4 nside");
-  if (spin != 0 && spin != 2) {
-    hcu_set_error("spin-%d maps not yet supported", spin);
-    return HCU_ERR_UNSUPPORTED;
-  }
-  HCU_ARG(nmaps >= 1, "nmaps >= 1");
-  HCU_ARG(spin == 0 || (nmaps % 2) == 0, "spin-2 input needs (Q,U) pairs");
-  return HCU_OK;
-}
-
-extern "C" int hcu_map2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
-                           const double *maps, int64_t map_stride,
-                           const double *ring_weights, const double *pixel_weights,
-                           int niter, const double *fl, void *alm_v, int64_t alm_stride) {
-  HCU_CHECK(check_sht_args(ctx, nside, lmax, spin, nmaps));
-  HCU_ARG(maps && alm_v && niter >= 0, "null pointer / niter");
-  HCU_CUDA(cudaSetDevice(ctx->device));
-  const i64 npix = 12 * nside * nside;
-  const i64 nalm = (i64)(lmax + 1) * (lmax + 2) / 2;
-  HCU_ARG(map_stride >= npix && alm_stride >= nalm, "strides");
-  hcu_geom *g;
-  hcu_coef *cf;
-  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
-  HCU_CHECK(hcu_get_coef(ctx, lmax, spin, &cf));
-
-  // small tables
-  HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_state, sizeof(double) * (size_t)(lmax + 1 + 2 * nside + 16)));
-  const double *dfl, *drw;
-  HCU_CHECK(upload_small(ctx, fl, lmax + 1, 0, &dfl));
-  HCU_CHECK(upload_small(ctx, ring_weights, 2 * nside, lmax + 1, &drw));
-
-  // inputs / outputs that live on the host are mirrored on the device
-  const double *dmaps = maps;
-  i64 dms = map_stride;
-  if (!dev_accessible(ptr_kind(maps))) {
-    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_map, sizeof(double) * npix * nmaps));
-    for (int c = 0; c < nmaps; ++c)
-      HCU_CUDA(cudaMemcpyAsync((double *)ctx->ws_map.ptr + (i64)c * npix, maps + (i64)c * map_stride,
-                               sizeof(double) * npix, cudaMemcpyDefault, ctx->stream));
-    dmaps = (double *)ctx->ws_map.ptr;
-    dms = npix;
-  }
-  const double *dpw = pixel_weights;
-  hcu_buffer pwbuf;
-  if (pixel_weights && !dev_accessible(ptr_kind(pixel_weights))) {
-    HCU_CHECK(hcu_ws_reserve(ctx, &pwbuf, sizeof(double) * npix));
-    HCU_CUDA(cudaMemcpyAsync(pwbuf.ptr, pixel_weights, sizeof(double) * npix, cudaMemcpyDefault, ctx->stream));
-    dpw = (double *)pwbuf.ptr;
-  }
-  double *dalm = (double *)alm_v;
-  i64 das = alm_stride;
-  const bool host_alm = !dev_accessible(ptr_kind(alm_v));
-  if (host_alm) {
-    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_alm, sizeof(double) * 2 * nalm * nmaps));
-    dalm = (double *)ctx->ws_alm.ptr;
-    das = nalm;
-  }
-  for (int c = 0; c < nmaps; ++c)
-    HCU_CUDA(cudaMemsetAsync(dalm + 2 * (i64)c * das, 0, sizeof(double) * 2 * nalm, ctx->stream));
-  HCU_CUDA(cudaMemsetAsync(ctx->work_counters, 0, 2 * sizeof(double), ctx->stream));
-  for (int i = 0; i < 4; ++i) ctx->sht_ms[i] = 0;
-
-  int rc = analysis_pass(ctx, g, cf, lmax, spin, nmaps, dmaps, dms, drw, dpw,
-                         niter == 0 ? dfl : nullptr, dalm, das, &ctx->sht_ms[0], &ctx->sht_ms[1]);
-  if (rc == HCU_OK && niter > 0) {
-    hcu_buffer resid;
-    rc = hcu_ws_reserve(ctx, &resid, sizeof(double) * npix * nmaps);
-    for (int it = 0; it < niter && rc == HCU_OK; ++it) {
-      double *r = (double *)resid.ptr;
-      rc = synthesis_pass(ctx, g, cf, lmax, spin, nmaps, dalm, das, r, npix, &ctx->sht_ms[2], &ctx->sht_ms[3]);
-      if (rc != HCU_OK) break;
-      for (int c = 0; c < nmaps; ++c) {
-        i64 b = (npix + 255) / 256;
-        if (b > (i64)ctx->num_sms * 8) b = (i64)ctx->num_sms * 8;
-        sub_kernel<<<(unsigned)b, 256, 0, ctx->stream>>>(r + (i64)c * npix, dmaps + (i64)c * dms,
-                                                         r + (i64)c * npix, npix);
-        ctx->n_launch++;
-      }
-      rc = analysis_pass(ctx, g, cf, lmax, spin, nmaps, r, npix, drw, dpw, nullptr, dalm, das,
-                         &ctx->sht_ms[0], &ctx->sht_ms[1]);
-    }
-    if (rc == HCU_OK && dfl) {
-      dim3 grid(lmax + 1, std::min(nmaps, 64));
-      almxfl_kernel<<<grid, 128, 0, ctx->stream>>>((double2 *)dalm, das, nmaps, lmax, dfl);
-      ctx->n_launch++;
-    }
-    cudaStreamSynchronize(ctx->stream);
-    free_buffer(&resid);
-  }
-  if (rc == HCU_OK && host_alm) {
-    for (int c = 0; c < nmaps && rc == HCU_OK; ++c)
-      if (cudaMemcpyAsync((double *)alm_v + 2 * (i64)c * alm_stride, dalm + 2 * (i64)c * das,
-                          sizeof(double) * 2 * nalm, cudaMemcpyDefault, ctx->stream) != cudaSuccess)
-        rc = HCU_ERR_CUDA;
-  }
-  cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  free_buffer(&pwbuf);
-  if (rc == HCU_OK && e != cudaSuccess) {
-    hcu_set_error("hcu_map2alm: %s", cudaGetErrorString(e));
-    rc = HCU_ERR_CUDA;
-  }
-  return rc;
-}
-
-extern "C" int hcu_alm2map(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
-                           const void *alm_v, int64_t alm_stride, double *maps,
-                           int64_t map_stride) {
-  HCU_CHECK(check_sht_args(ctx, nside, lmax, spin, nmaps));
-  HCU_ARG(maps && alm_v, "null pointer");
-  HCU_CUDA(cudaSetDevice(ctx->device));
-  const i64 npix = 12 * nside * nside;
-  const i64 nalm = (i64)(lmax + 1) * (lmax + 2) / 2;
-  HCU_ARG(map_stride >= npix && alm_stride >= nalm, "strides");
-  hcu_geom *g;
-  hcu_coef *cf;
-  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
-  HCU_CHECK(hcu_get_coef(ctx, lmax, spin, &cf));
-  const double *dalm = (const double *)alm_v;
-  i64 das = alm_stride;
-  if (!dev_accessible(ptr_kind(alm_v))) {
-    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_alm, sizeof(double) * 2 * nalm * nmaps));
-    for (int c = 0; c < nmaps; ++c)
-      HCU_CUDA(cudaMemcpyAsync((double *)ctx->ws_alm.ptr + 2 * (i64)c * nalm,
-                               (const double *)alm_v + 2 * (i64)c * alm_stride,
-                               sizeof(double) * 2 * nalm, cudaMemcpyDefault, ctx->stream));
-    dalm = (double *)ctx->ws_alm.ptr;
-    das = nalm;
-  }
-  double *dmaps = maps;
-  i64 dms = map_stride;
-  const bool host_maps = !dev_accessible(ptr_kind(maps));
-  if (host_maps) {
-    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_map, sizeof(double) * npix * nmaps));
-    dmaps = (double *)ctx->ws_map.ptr;
-    dms = npix;
-  }
-  ctx->sht_ms[2] = ctx->sht_ms[3] = 0;
-  HCU_CHECK(synthesis_pass(ctx, g, cf, lmax, spin, nmaps, dalm, das, dmaps, dms, &ctx->sht_ms[2], &ctx->sht_ms[3]));
-  if (host_maps)
-    for (int c = 0; c < nmaps; ++c)
-      HCU_CUDA(cudaMemcpyAsync(maps + (i64)c * map_stride, dmaps + (i64)c * dms, sizeof(double) * npix,
-                               cudaMemcpyDefault, ctx->stream));
-  HCU_CUDA(cudaStreamSynchronize(ctx->stream));
-  return HCU_OK;
-}
-
-extern "C" int hcu_map2phase(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp,
-                             const double *maps, int64_t map_stride,
-                             const double *ring_weights, int64_t rp_lo, int64_t rp_hi,
-                             double *phase) {
-  HCU_CHECK(check_sht_args(ctx, nside, lmax, 0, ncomp));
-  HCU_ARG(maps && phase, "null pointer");
-  HCU_ARG(0 <= rp_lo && rp_lo <= rp_hi && rp_hi <= 2 * nside, "ring pair range");
-  HCU_ARG(dev_accessible(ptr_kind(maps)) && dev_accessible(ptr_kind(phase)), "device pointers required");
-  HCU_ARG(!ring_weights || dev_accessible(ptr_kind(ring_weights)), "ring_weights must be on the device");
-  HCU_CUDA(cudaSetDevice(ctx->device));
-  hcu_geom *g;
-  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
-  return hcu_ring_fft_forward(ctx, g, lmax, ncomp, maps, map_stride, ring_weights, rp_lo, rp_hi, phase);
-}
-
-extern "C" int hcu_phase2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
-                             const double *phase, const int32_t *mlist, int nm,
-                             int64_t rp_lo, int64_t rp_hi, const double *fl, void *alm,
-                             int64_t alm_stride) {
-  HCU_CHECK(check_sht_args(ctx, nside, lmax, spin, ncomp));
-  HCU_ARG(phase && alm && nm >= 0, "null pointer");
-  HCU_ARG(0 <= rp_lo && rp_lo <= rp_hi && rp_hi <= 2 * nside, "ring pair range");
-  HCU_ARG(dev_accessible(ptr_kind(phase)) && dev_accessible(ptr_kind(alm)), "device pointers required");
-  HCU_ARG(!mlist || dev_accessible(ptr_kind(mlist)), "mlist must be on the device");
-  HCU_ARG(!fl || dev_accessible(ptr_kind(fl)), "fl must be on the device");
-  HCU_CUDA(cudaSetDevice(ctx->device));
-  hcu_geom *g;
-  hcu_coef *cf;
-  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
-  HCU_CHECK(hcu_get_coef(ctx, lmax, spin, &cf));
-  return hcu_legendre_analysis(ctx, g, cf, lmax, spin, ncomp, phase, mlist, nm, rp_lo, rp_hi, fl,
-                               (double *)alm, alm_stride);
-}
 
 extern "C" int hcu_last_sht_timing(hcu_ctx *ctx, float ms[4]) {
   HCU_ARG(ctx && ms, "hcu_last_sht_timing");

@@ -55,6 +55,13 @@ void hcu_set_error(const char *fmt, ...);
     HCU_CUDA(cudaGetLastError());                                             \
   } while (0)
 
+// up to HCU_MAX_BATCH row pointers passed to kernels by value (maps or alm rows
+// of one transform batch need not be contiguous in memory)
+#define HCU_MAX_BATCH 12
+struct hcu_ptrs {
+  double *p[HCU_MAX_BATCH];
+};
+
 // a growable device workspace
 struct hcu_buffer {
   void *ptr = nullptr;
@@ -125,19 +132,17 @@ int hcu_launch_map_values(hcu_ctx *ctx, i64 nside, int scheme, const double *lon
                           i64 *ipix_out);
 int hcu_build_bluestein(hcu_ctx *ctx, hcu_geom *g);
 int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
-                         const double *maps, i64 map_stride,
-                         const double *ring_weights, i64 rp_lo, i64 rp_hi,
-                         double *phase);
+                         const hcu_ptrs &maps, const double *ring_weights,
+                         i64 rp_lo, i64 rp_hi, double *phase);
 int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
-                         const double *phase, double *maps, i64 map_stride);
+                         const double *phase, const hcu_ptrs &maps);
 int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c);
 int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
                           int spin, int ncomp, const double *phase,
                           const int32_t *mlist_dev, int nm, i64 rp_lo, i64 rp_hi,
-                          const double *fl_dev, double *alm, i64 alm_stride);
+                          const double *fl_dev, const hcu_ptrs &alm);
 int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
-                           int spin, int ncomp, const double *alm,
-                           i64 alm_stride, double *phase);
+                           int spin, int ncomp, const hcu_ptrs &alm, double *phase);
 
 static inline int ilog2_host(i64 v) {
   int r = 0;

@@ -1,0 +1,333 @@
+// hcu_transform.cu -- orchestration of the spherical-harmonic transform stages
+// (ring FFT <-> Legendre), batching over maps, Jacobi iterations, staging of
+// host-resident inputs/outputs.  See include/heracles_cuda.h.
+#include <algorithm>
+#include <vector>
+
+#include "hcu_common.cuh"
+
+int hcu_mul(hcu_ctx *ctx, double *out, const double *a, const double *b, i64 n);
+bool hcu_dev_accessible(const void *p);
+
+namespace {
+
+__global__ void almxfl_kernel(hcu_ptrs alm, int nrows, int lmax, const double *fl) {
+  const int m = blockIdx.x;
+  const i64 base = (i64)m * (2 * lmax + 1 - m) / 2;
+  for (int r = blockIdx.y; r < nrows; r += gridDim.y) {
+    double2 *row = reinterpret_cast<double2 *>(alm.p[r]);
+    for (int l = m + threadIdx.x; l <= lmax; l += blockDim.x) {
+      double2 v = row[base + l];
+      const double f = fl[l];
+      row[base + l] = make_double2(v.x * f, v.y * f);
+    }
+  }
+}
+
+__global__ void sub_kernel(double *out, const double *a, const double *b, i64 n) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  i64 s = (i64)gridDim.x * blockDim.x;
+  for (; i < n; i += s) out[i] = a[i] - b[i];
+}
+
+bool valid_nside(i64 nside) {
+  return nside >= 1 && nside <= (1 << 24) && (nside & (nside - 1)) == 0;
+}
+
+int check_sht_args(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps) {
+  HCU_ARG(ctx, "ctx");
+  HCU_ARG(valid_nside(nside) && nside <= 4096,
+          "nside must be a power of two <= 4096 (polar-cap FFT tile limit)");
+  HCU_ARG(lmax >= 0 && lmax <= 4 * nside, "0 <= lmax <= 4 nside");
+  if (spin != 0 && spin != 2) {
+    hcu_set_error("spin-%d maps not yet supported", spin);
+    return HCU_ERR_UNSUPPORTED;
+  }
+  HCU_ARG(nmaps >= 1, "nmaps >= 1");
+  HCU_ARG(spin == 0 || (nmaps % 2) == 0, "spin-2 input needs (Q,U) pairs");
+  return HCU_OK;
+}
+
+// small host arrays (fl, ring weights) are copied into ws_state; device arrays are used in place
+int upload_small(hcu_ctx *ctx, const double *src, size_t n, size_t slot_off, const double **dev) {
+  if (!src) {
+    *dev = nullptr;
+    return HCU_OK;
+  }
+  if (hcu_dev_accessible(src)) {
+    *dev = src;
+    return HCU_OK;
+  }
+  double *d = (double *)ctx->ws_state.ptr + slot_off;
+  HCU_CUDA(cudaMemcpyAsync(d, src, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  HCU_CUDA(cudaStreamSynchronize(ctx->stream));
+  *dev = d;
+  return HCU_OK;
+}
+
+struct StageTimer {
+  hcu_ctx *ctx;
+  cudaEvent_t a, b;
+  float *acc;
+  StageTimer(hcu_ctx *c, int i, float *dst) : ctx(c), a(c->ev[i]), b(c->ev[i + 1]), acc(dst) {
+    cudaEventRecord(a, ctx->stream);
+  }
+  void stop() { cudaEventRecord(b, ctx->stream); }
+  void collect() {
+    float t = 0;
+    if (cudaEventSynchronize(b) == cudaSuccess && cudaEventElapsedTime(&t, a, b) == cudaSuccess)
+      *acc += t;
+  }
+};
+
+// one analysis pass over nmaps rows: alm[c] += A(W maps[c])
+int analysis_pass(hcu_ctx *ctx, hcu_geom *g, hcu_coef *cf, int lmax, int spin, int nmaps,
+                  double *const *maps, const double *rw, const double *pw, const double *fl,
+                  double *const *alm) {
+  const i64 nside = g->nside;
+  const i64 npix = 12 * nside * nside;
+  const i64 nrp = g->nrp;
+  for (int c0 = 0; c0 < nmaps; c0 += HCU_MAX_BATCH) {
+    const int nb = std::min(HCU_MAX_BATCH, nmaps - c0);
+    hcu_ptrs src, dst;
+    for (int c = 0; c < HCU_MAX_BATCH; ++c) {
+      src.p[c] = c < nb ? maps[c0 + c] : nullptr;
+      dst.p[c] = c < nb ? alm[c0 + c] : nullptr;
+    }
+    if (pw) {
+      HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_misc, sizeof(double) * npix * nb));
+      for (int c = 0; c < nb; ++c) {
+        double *tmp = (double *)ctx->ws_misc.ptr + (i64)c * npix;
+        HCU_CHECK(hcu_mul(ctx, tmp, src.p[c], pw, npix));
+        src.p[c] = tmp;
+      }
+    }
+    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_phase, sizeof(double) * 4 * (size_t)(lmax + 1) * nrp * nb));
+    double *phase = (double *)ctx->ws_phase.ptr;
+    StageTimer t0(ctx, 0, &ctx->sht_ms[0]);
+    HCU_CHECK(hcu_ring_fft_forward(ctx, g, lmax, nb, src, rw, 0, nrp, phase));
+    t0.stop();
+    StageTimer t1(ctx, 2, &ctx->sht_ms[1]);
+    HCU_CHECK(hcu_legendre_analysis(ctx, g, cf, lmax, spin, nb, phase, nullptr, lmax + 1, 0, nrp, fl, dst));
+    t1.stop();
+    t0.collect();
+    t1.collect();
+  }
+  return HCU_OK;
+}
+
+// maps[c] = S(alm[c])
+int synthesis_pass(hcu_ctx *ctx, hcu_geom *g, hcu_coef *cf, int lmax, int spin, int nmaps,
+                   double *const *alm, double *const *maps) {
+  const i64 nrp = g->nrp;
+  for (int c0 = 0; c0 < nmaps; c0 += HCU_MAX_BATCH) {
+    const int nb = std::min(HCU_MAX_BATCH, nmaps - c0);
+    hcu_ptrs src, dst;
+    for (int c = 0; c < HCU_MAX_BATCH; ++c) {
+      src.p[c] = c < nb ? alm[c0 + c] : nullptr;
+      dst.p[c] = c < nb ? maps[c0 + c] : nullptr;
+    }
+    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_phase, sizeof(double) * 4 * (size_t)(lmax + 1) * nrp * nb));
+    double *phase = (double *)ctx->ws_phase.ptr;
+    StageTimer t0(ctx, 0, &ctx->sht_ms[2]);
+    HCU_CHECK(hcu_legendre_synthesis(ctx, g, cf, lmax, spin, nb, src, phase));
+    t0.stop();
+    StageTimer t1(ctx, 2, &ctx->sht_ms[3]);
+    HCU_CHECK(hcu_ring_fft_inverse(ctx, g, lmax, nb, phase, dst));
+    t1.stop();
+    t0.collect();
+    t1.collect();
+  }
+  return HCU_OK;
+}
+
+}  // namespace
+
+extern "C" int hcu_map2alm_many(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
+                                const double *const *maps, const double *ring_weights,
+                                const double *pixel_weights, int niter, const double *fl,
+                                void *const *alm) {
+  HCU_CHECK(check_sht_args(ctx, nside, lmax, spin, nmaps));
+  HCU_ARG(maps && alm && niter >= 0, "null pointer / niter");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  const i64 npix = 12 * nside * nside;
+  const i64 nalm = (i64)(lmax + 1) * (lmax + 2) / 2;
+  hcu_geom *g;
+  hcu_coef *cf;
+  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
+  HCU_CHECK(hcu_get_coef(ctx, lmax, spin, &cf));
+
+  HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_state, sizeof(double) * (size_t)(lmax + 1 + 2 * nside + 16)));
+  const double *dfl, *drw;
+  HCU_CHECK(upload_small(ctx, fl, lmax + 1, 0, &dfl));
+  HCU_CHECK(upload_small(ctx, ring_weights, 2 * nside, lmax + 1, &drw));
+
+  // rows that live on the host are mirrored on the device
+  std::vector<double *> dmaps(nmaps), dalm(nmaps);
+  int nhost_maps = 0, nhost_alm = 0;
+  for (int c = 0; c < nmaps; ++c) {
+    HCU_ARG(maps[c] && alm[c], "null row pointer");
+    if (!hcu_dev_accessible(maps[c])) ++nhost_maps;
+    if (!hcu_dev_accessible(alm[c])) ++nhost_alm;
+  }
+  if (nhost_maps) HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_map, sizeof(double) * npix * nhost_maps));
+  if (nhost_alm) HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_alm, sizeof(double) * 2 * nalm * nhost_alm));
+  for (int c = 0, im = 0, ia = 0; c < nmaps; ++c) {
+    if (hcu_dev_accessible(maps[c])) {
+      dmaps[c] = const_cast<double *>(maps[c]);
+    } else {
+      dmaps[c] = (double *)ctx->ws_map.ptr + (i64)(im++) * npix;
+      HCU_CUDA(cudaMemcpyAsync(dmaps[c], maps[c], sizeof(double) * npix, cudaMemcpyDefault, ctx->stream));
+    }
+    dalm[c] = hcu_dev_accessible(alm[c]) ? (double *)alm[c]
+                                         : (double *)ctx->ws_alm.ptr + 2 * (i64)(ia++) * nalm;
+    HCU_CUDA(cudaMemsetAsync(dalm[c], 0, sizeof(double) * 2 * nalm, ctx->stream));
+  }
+  const double *dpw = pixel_weights;
+  hcu_buffer pwbuf, resid;
+  if (pixel_weights && !hcu_dev_accessible(pixel_weights)) {
+    HCU_CHECK(hcu_ws_reserve(ctx, &pwbuf, sizeof(double) * npix));
+    HCU_CUDA(cudaMemcpyAsync(pwbuf.ptr, pixel_weights, sizeof(double) * npix, cudaMemcpyDefault, ctx->stream));
+    dpw = (double *)pwbuf.ptr;
+  }
+  HCU_CUDA(cudaMemsetAsync(ctx->work_counters, 0, 2 * sizeof(double), ctx->stream));
+  for (int i = 0; i < 4; ++i) ctx->sht_ms[i] = 0;
+
+  int rc = analysis_pass(ctx, g, cf, lmax, spin, nmaps, dmaps.data(), drw, dpw,
+                         niter == 0 ? dfl : nullptr, dalm.data());
+  if (rc == HCU_OK && niter > 0) {
+    // Jacobi refinement in batches so the residual buffer stays small
+    const int cap = HCU_MAX_BATCH;
+    rc = hcu_ws_reserve(ctx, &resid, sizeof(double) * npix * std::min(cap, nmaps));
+    for (int c0 = 0; c0 < nmaps && rc == HCU_OK; c0 += cap) {
+      const int nb = std::min(cap, nmaps - c0);
+      std::vector<double *> r(nb);
+      for (int c = 0; c < nb; ++c) r[c] = (double *)resid.ptr + (i64)c * npix;
+      for (int it = 0; it < niter && rc == HCU_OK; ++it) {
+        rc = synthesis_pass(ctx, g, cf, lmax, spin, nb, dalm.data() + c0, r.data());
+        if (rc != HCU_OK) break;
+        for (int c = 0; c < nb; ++c) {
+          i64 b = std::min<i64>((npix + 255) / 256, (i64)ctx->num_sms * 8);
+          sub_kernel<<<(unsigned)b, 256, 0, ctx->stream>>>(r[c], dmaps[c0 + c], r[c], npix);
+          ctx->n_launch++;
+        }
+        rc = analysis_pass(ctx, g, cf, lmax, spin, nb, r.data(), drw, dpw, nullptr, dalm.data() + c0);
+      }
+      if (rc == HCU_OK && dfl) {
+        hcu_ptrs rows;
+        for (int c = 0; c < HCU_MAX_BATCH; ++c) rows.p[c] = c < nb ? dalm[c0 + c] : nullptr;
+        dim3 grid(lmax + 1, nb);
+        almxfl_kernel<<<grid, 128, 0, ctx->stream>>>(rows, nb, lmax, dfl);
+        ctx->n_launch++;
+      }
+    }
+  }
+  if (rc == HCU_OK)
+    for (int c = 0; c < nmaps; ++c)
+      if (dalm[c] != (double *)alm[c] &&
+          cudaMemcpyAsync(alm[c], dalm[c], sizeof(double) * 2 * nalm, cudaMemcpyDefault, ctx->stream) != cudaSuccess)
+        rc = HCU_ERR_CUDA;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (pwbuf.ptr) cudaFree(pwbuf.ptr);
+  if (resid.ptr) cudaFree(resid.ptr);
+  if (rc == HCU_OK && e != cudaSuccess) {
+    hcu_set_error("hcu_map2alm: %s", cudaGetErrorString(e));
+    rc = HCU_ERR_CUDA;
+  }
+  return rc;
+}
+
+extern "C" int hcu_map2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
+                           const double *maps, int64_t map_stride,
+                           const double *ring_weights, const double *pixel_weights,
+                           int niter, const double *fl, void *alm_v, int64_t alm_stride) {
+  HCU_ARG(ctx && maps && alm_v && nmaps >= 1, "hcu_map2alm: null pointer");
+  HCU_ARG(map_stride >= 12 * nside * nside, "map_stride");
+  HCU_ARG(alm_stride >= (int64_t)(lmax + 1) * (lmax + 2) / 2, "alm_stride");
+  std::vector<const double *> mp(nmaps);
+  std::vector<void *> ap(nmaps);
+  for (int c = 0; c < nmaps; ++c) {
+    mp[c] = maps + (i64)c * map_stride;
+    ap[c] = (double *)alm_v + 2 * (i64)c * alm_stride;
+  }
+  return hcu_map2alm_many(ctx, nside, lmax, spin, nmaps, mp.data(), ring_weights, pixel_weights,
+                          niter, fl, ap.data());
+}
+
+extern "C" int hcu_alm2map(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
+                           const void *alm_v, int64_t alm_stride, double *maps,
+                           int64_t map_stride) {
+  HCU_CHECK(check_sht_args(ctx, nside, lmax, spin, nmaps));
+  HCU_ARG(maps && alm_v, "null pointer");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  const i64 npix = 12 * nside * nside;
+  const i64 nalm = (i64)(lmax + 1) * (lmax + 2) / 2;
+  HCU_ARG(map_stride >= npix && alm_stride >= nalm, "strides");
+  hcu_geom *g;
+  hcu_coef *cf;
+  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
+  HCU_CHECK(hcu_get_coef(ctx, lmax, spin, &cf));
+  std::vector<double *> dalm(nmaps), dmaps(nmaps);
+  const bool host_alm = !hcu_dev_accessible(alm_v), host_maps = !hcu_dev_accessible(maps);
+  if (host_alm) HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_alm, sizeof(double) * 2 * nalm * nmaps));
+  if (host_maps) HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_map, sizeof(double) * npix * nmaps));
+  for (int c = 0; c < nmaps; ++c) {
+    const double *src = (const double *)alm_v + 2 * (i64)c * alm_stride;
+    if (host_alm) {
+      dalm[c] = (double *)ctx->ws_alm.ptr + 2 * (i64)c * nalm;
+      HCU_CUDA(cudaMemcpyAsync(dalm[c], src, sizeof(double) * 2 * nalm, cudaMemcpyDefault, ctx->stream));
+    } else {
+      dalm[c] = const_cast<double *>(src);
+    }
+    dmaps[c] = host_maps ? (double *)ctx->ws_map.ptr + (i64)c * npix : maps + (i64)c * map_stride;
+  }
+  ctx->sht_ms[2] = ctx->sht_ms[3] = 0;
+  HCU_CHECK(synthesis_pass(ctx, g, cf, lmax, spin, nmaps, dalm.data(), dmaps.data()));
+  if (host_maps)
+    for (int c = 0; c < nmaps; ++c)
+      HCU_CUDA(cudaMemcpyAsync(maps + (i64)c * map_stride, dmaps[c], sizeof(double) * npix,
+                               cudaMemcpyDefault, ctx->stream));
+  HCU_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HCU_OK;
+}
+
+extern "C" int hcu_map2phase(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp,
+                             const double *maps, int64_t map_stride,
+                             const double *ring_weights, int64_t rp_lo, int64_t rp_hi,
+                             double *phase) {
+  HCU_CHECK(check_sht_args(ctx, nside, lmax, 0, ncomp));
+  HCU_ARG(maps && phase, "null pointer");
+  HCU_ARG(ncomp <= HCU_MAX_BATCH, "at most 10 components per call");
+  HCU_ARG(0 <= rp_lo && rp_lo <= rp_hi && rp_hi <= 2 * nside, "ring pair range");
+  HCU_ARG(hcu_dev_accessible(maps) && hcu_dev_accessible(phase), "device pointers required");
+  HCU_ARG(!ring_weights || hcu_dev_accessible(ring_weights), "ring_weights must be on the device");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  hcu_geom *g;
+  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
+  hcu_ptrs src;
+  for (int c = 0; c < HCU_MAX_BATCH; ++c)
+    src.p[c] = c < ncomp ? const_cast<double *>(maps) + (i64)c * map_stride : nullptr;
+  return hcu_ring_fft_forward(ctx, g, lmax, ncomp, src, ring_weights, rp_lo, rp_hi, phase);
+}
+
+extern "C" int hcu_phase2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
+                             const double *phase, const int32_t *mlist, int nm,
+                             int64_t rp_lo, int64_t rp_hi, const double *fl, void *alm,
+                             int64_t alm_stride) {
+  HCU_CHECK(check_sht_args(ctx, nside, lmax, spin, ncomp));
+  HCU_ARG(phase && alm && nm >= 0, "null pointer");
+  HCU_ARG(ncomp <= HCU_MAX_BATCH, "at most 10 components per call");
+  HCU_ARG(0 <= rp_lo && rp_lo <= rp_hi && rp_hi <= 2 * nside, "ring pair range");
+  HCU_ARG(hcu_dev_accessible(phase) && hcu_dev_accessible(alm), "device pointers required");
+  HCU_ARG(!mlist || hcu_dev_accessible(mlist), "mlist must be on the device");
+  HCU_ARG(!fl || hcu_dev_accessible(fl), "fl must be on the device");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  hcu_geom *g;
+  hcu_coef *cf;
+  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
+  HCU_CHECK(hcu_get_coef(ctx, lmax, spin, &cf));
+  hcu_ptrs rows;
+  for (int c = 0; c < HCU_MAX_BATCH; ++c)
+    rows.p[c] = c < ncomp ? (double *)alm + 2 * (i64)c * alm_stride : nullptr;
+  return hcu_legendre_analysis(ctx, g, cf, lmax, spin, ncomp, phase, mlist, nm, rp_lo, rp_hi, fl, rows);
+}

@@ -102,8 +102,8 @@ __global__ void bluestein_filter_kernel(int ilo, int M, double2 *bfilt, const i6
 }
 
 // forward: one block per (cap ring pair i, component)
-__global__ void cap_fft_fwd_kernel(int ilo, int M, i64 nside, const double *maps,
-                                   i64 map_stride, const double2 *bfilt,
+__global__ void cap_fft_fwd_kernel(int ilo, int M, i64 nside, hcu_ptrs maps,
+                                   const double2 *bfilt,
                                    const i64 *off, double2 *Y, i64 ncap) {
   extern __shared__ double2 smem[];
   double2 *a = smem;
@@ -113,8 +113,8 @@ __global__ void cap_fft_fwd_kernel(int ilo, int M, i64 nside, const double *maps
   const i64 npix = 12 * nside * nside;
   const i64 startN = 2LL * i * (i - 1);
   const i64 startS = npix - startN - 4LL * i;
-  const double *mN = maps + (i64)c * map_stride + startN;
-  const double *mS = maps + (i64)c * map_stride + startS;
+  const double *mN = maps.p[c] + startN;
+  const double *mS = maps.p[c] + startS;
   const double2 *B = bfilt + off[i];
   double2 *Yc = Y + (i64)c * ncap + startN;
   make_twiddles(tw, M);
@@ -262,7 +262,7 @@ __global__ void belt_pre_inv_kernel(i64 nside, int lmax, int ncomp, int comp,
 __global__ void cap_fft_inv_kernel(int ilo, int M, i64 nside, int lmax, int ncomp,
                                    int comp, const double *phase,
                                    const double2 *bfilt, const i64 *off,
-                                   double *maps, i64 map_stride) {
+                                   hcu_ptrs maps) {
   extern __shared__ double2 smem[];
   double2 *a = smem;
   double2 *tw = smem + M;
@@ -273,8 +273,8 @@ __global__ void cap_fft_inv_kernel(int ilo, int M, i64 nside, int lmax, int ncom
   const i64 rp = i - 1;
   const i64 startN = 2LL * i * (i - 1);
   const i64 startS = npix - startN - 4LL * i;
-  double *mN = maps + (i64)comp * map_stride + startN;
-  double *mS = maps + (i64)comp * map_stride + startS;
+  double *mN = maps.p[comp] + startN;
+  double *mS = maps.p[comp] + startS;
   const double2 *B = bfilt + off[i];
   make_twiddles(tw, M);
   __syncthreads();
@@ -405,9 +405,8 @@ static int get_belt_plan(hcu_ctx *ctx, std::map<i64, cufftHandle> &cache, i64 ns
 
 // forward ring FFT stage for ring pairs [rp_lo, rp_hi) of ncomp maps
 int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
-                         const double *maps, i64 map_stride,
-                         const double *ring_weights, i64 rp_lo, i64 rp_hi,
-                         double *phase) {
+                         const hcu_ptrs &maps, const double *ring_weights,
+                         i64 rp_lo, i64 rp_hi, double *phase) {
   const i64 nside = g->nside;
   const i64 ncap = 2 * nside * (nside - 1);
   const i64 nrp_local = rp_hi - rp_lo;
@@ -432,7 +431,7 @@ int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       dim3 grid(ihi - i + 1, ncomp);
       cap_fft_fwd_kernel<<<grid, cap_threads(M), smem, ctx->stream>>>(
-          i, M, nside, maps, map_stride, g->bfilt, g->bfilt_off, Y, ncap);
+          i, M, nside, maps, g->bfilt, g->bfilt_off, Y, ncap);
       HCU_LAUNCH_CHECK(ctx);
       i = ihi + 1;
     }
@@ -452,7 +451,7 @@ int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
     HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_belt, sizeof(double2) * (size_t)nk * (2 * nside + 1)));
     double2 *X = (double2 *)ctx->ws_belt.ptr;
     for (int c = 0; c < ncomp; ++c) {
-      HCU_CUFFT(cufftExecD2Z(plan, const_cast<double *>(maps + (i64)c * map_stride + ncap),
+      HCU_CUFFT(cufftExecD2Z(plan, maps.p[c] + ncap,
                              reinterpret_cast<cufftDoubleComplex *>(X)));
       ctx->n_cufft++;
       dim3 grid(mblocks, (unsigned)(belt_hi - belt_lo));
@@ -466,7 +465,7 @@ int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
 
 // inverse ring FFT stage (all ring pairs), phase rows are (reN, imN, reS, imS)
 int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
-                         const double *phase, double *maps, i64 map_stride) {
+                         const double *phase, const hcu_ptrs &maps) {
   const i64 nside = g->nside;
   const i64 ncap = 2 * nside * (nside - 1);
   const int n4 = (int)(4 * nside);
@@ -482,7 +481,7 @@ int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
       HCU_CUDA(cudaFuncSetAttribute(cap_fft_inv_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cap_fft_inv_kernel<<<ihi - i + 1, cap_threads(M), smem, ctx->stream>>>(
-          i, M, nside, lmax, ncomp, c, phase, g->bfilt, g->bfilt_off, maps, map_stride);
+          i, M, nside, lmax, ncomp, c, phase, g->bfilt, g->bfilt_off, maps);
       HCU_LAUNCH_CHECK(ctx);
       i = ihi + 1;
     }
@@ -497,7 +496,7 @@ int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
     belt_pre_inv_kernel<<<grid, 128, 0, ctx->stream>>>(nside, lmax, ncomp, c, phase, X);
     HCU_LAUNCH_CHECK(ctx);
     HCU_CUFFT(cufftExecZ2D(plan, reinterpret_cast<cufftDoubleComplex *>(X),
-                           maps + (i64)c * map_stride + ncap));
+                           maps.p[c] + ncap));
     ctx->n_cufft++;
   }
   return HCU_OK;

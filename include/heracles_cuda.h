@@ -124,6 +124,15 @@ int hcu_map2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
                 const double *ring_weights, const double *pixel_weights,
                 int niter, const double *fl, void *alm, int64_t alm_stride);
 
+/* Same transform for rows that are NOT contiguous in memory: maps[c] / alm[c]
+ * are per-row pointers.  This is what lets one call batch the maps of many
+ * fields (heracles/mapping.py:151-171 transforms them one at a time) so that
+ * the Legendre recursion is shared by up to 10 maps. */
+int hcu_map2alm_many(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
+                     const double *const *maps, const double *ring_weights,
+                     const double *pixel_weights, int niter, const double *fl,
+                     void *const *alm);
+
 /* hp.alm2map, the synthesis used inside map2alm's iterations (also exported) */
 int hcu_alm2map(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
                 const void *alm, int64_t alm_stride, double *maps,

@@ -129,7 +129,7 @@ def test_round_trip_with_iterations(oracle, spin):
     b3 = oracle.map2alm(nside, lmax, m, spin=spin, niter=3)
     e0 = np.abs(b0 - a).max()
     e3 = np.abs(b3 - a).max()
-    assert e3 < 1e-6 and e3 < e0 * 1e-2
+    assert e3 < 1e-5 and e3 < e0 * 1e-2
 
 
 def test_scaled_recursion_large_m(oracle):
