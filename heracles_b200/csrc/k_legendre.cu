@@ -1,38 +1,31 @@
-// k_legendre.cu -- FP64 Legendre stage of the spherical-harmonic analysis
-// (and synthesis) on HEALPix ring pairs, spin 0 and spin 2, batched over maps.
+// k_legendre.cu -- FP64 Legendre stage of the spherical-harmonic SYNTHESIS
+// (alm -> ring Fourier coefficients) on HEALPix ring pairs, spin 0 and spin 2,
+// batched over up to 12 components; plus the recursion coefficient tables
+// shared with the analysis kernel (k_legendre_ana.cu).
 //
-// Replaces the libsharp/ducc Legendre loops behind hp.map2alm / hp.alm2map
-// (heracles/healpy.py:183-189).  FP64 FMA bound.
+// Replaces the libsharp/ducc Legendre loop behind hp.alm2map, which healpy's
+// map2alm runs inside its default iter=3 refinement (heracles/healpy.py:183-189).
+// FP64 FMA bound.
 //
-// Analysis kernel design (one CTA = one m and one group of 256 ring pairs,
-// 8 warps, one warp = 32 ring pairs, one lane = one ring pair):
-//   phase A  every lane advances its own lambda_lm(theta) three-term recursion
-//            over a chunk of LC consecutive l (scaled arithmetic while the
-//            value is below 2^-200) and writes the values into a per-warp
-//            shared-memory tile  Lam[parity][ring][l].
-//   phase B  the same warp re-reads that tile as the A operand of a small
-//            register-blocked FP64 "GEMM"  out[l][col] += Lam[l][ring] * F[ring][col]
-//            where F (the ring Fourier coefficients of all maps of the batch
-//            for this m, north+south and north-south combinations) was staged
-//            in shared memory once per CTA.  Lane tile = 8 l x 5 columns.
-//   flush    the 8 warps' partial tiles are summed through shared memory and
-//            added to alm with one RED.ADD.F64 per output (x fl[l] fused).
-// The recursion cost (about 4 flops per (l, ring)) is shared by all maps of the
-// batch; the accumulate cost is 4 flops per (l, ring, map) for spin 0 and
-// 16 per spin-2 field.
+// One lane = one ring pair: it advances its own lambda_lm(theta) recursion in l
+// and accumulates  b_m(theta) = sum_l a_lm lambda_lm(theta)  for every component
+// of the batch in registers, so there is no cross-lane reduction.  The a_lm and
+// the recursion coefficients of a chunk of l are staged once per CTA in shared
+// memory and read as warp-wide broadcasts.  North and south rings share the
+// recursion through lambda_lm(pi - theta) = (-1)^(l+m) lambda_lm(theta): spin 0
+// keeps separate even / odd (l+m) accumulators and forms N = E + O, S = E - O at
+// the end, which halves the FMAs.
 #include "legendre_common.cuh"
 
 namespace {
 
-// ---------------------------------------------------------------------------
-// synthesis: one lane = one ring pair, loops over l, alm broadcast from smem.
 // phase out: [(m * nrp + rp) * ncomp + c] * 4 = (reN, imN, reS, imS)
-// ---------------------------------------------------------------------------
 template <int SPIN, int NB>
 __global__ void __launch_bounds__(128) legendre_synthesis_kernel(LegArgs a, double *phase_out) {
-  // smem: alm chunk [LCH][NB][2]
-  constexpr int LCH = 64;
-  __shared__ double s_alm[LCH * NB * 2];
+  constexpr int LCH = 32;                     // l per staged chunk (even)
+  constexpr int CW = SPIN == 0 ? 2 : 4;       // doubles per coefficient entry
+  __shared__ __align__(16) double2 s_alm[LCH * NB];
+  __shared__ __align__(16) double s_coef[LCH * CW];
   const int ngroups = (int)((a.nrp_local + 127) / 128);
   const int g = blockIdx.x % ngroups;
   const int m = blockIdx.x / ngroups;
@@ -47,10 +40,17 @@ __global__ void __launch_bounds__(128) legendre_synthesis_kernel(LegArgs a, doub
     chh = a.ch[rp];
     shh = a.sh[rp];
   }
-  // north and south accumulators per component (complex)
-  double aN[NB][2], aS[NB][2];
+  // spin 0: acc[q][c] with q = parity slot (even/odd step inside a chunk)
+  // spin 2: acc[0] = sum lam+ 2a, acc[1] = sum lam- -2a (north); acc[2], acc[3] the southern sums
+  constexpr int NACC = SPIN == 0 ? 2 : 4;
+  constexpr int NCOL = SPIN == 0 ? NB : (NB + 1) / 2;
+  double acc[NACC][NCOL][2];
 #pragma unroll
-  for (int c = 0; c < NB; ++c) aN[c][0] = aN[c][1] = aS[c][0] = aS[c][1] = 0.0;
+  for (int q = 0; q < NACC; ++q)
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) acc[q][c][0] = acc[q][c][1] = 0.0;
+  const int pb = (l0 + m) & 1;
+
   if (l0 <= lmax) {
     const bool alive = valid && !ring_is_dead(lmax, m, SPIN, x, sth);
     LamState sp, sm;
@@ -60,83 +60,139 @@ __global__ void __launch_bounds__(128) legendre_synthesis_kernel(LegArgs a, doub
     const i64 cbase = alm_index(lmax, 0, m);
     for (int lc = l0; lc <= lmax; lc += LCH) {
       __syncthreads();
-      for (int idx = threadIdx.x; idx < LCH * NB * 2; idx += 128) {
-        int li = idx / (NB * 2), r = idx - li * NB * 2;
-        int c = r >> 1, ri = r & 1;
-        int l = lc + li;
-        double v = 0.0;
-        if (l <= lmax && c < a.ncomp)
-          v = a.alm.p[c][2 * (cbase + l) + ri];
-        s_alm[idx] = v;
+      // ---- stage a_lm and coefficients of l = lc .. lc + LCH - 1 ----
+      if (SPIN == 0) {
+        for (int idx = threadIdx.x; idx < LCH * NB; idx += 128) {
+          const int li = idx / NB, c = idx - li * NB;
+          const int l = lc + li;
+          double2 v = make_double2(0., 0.);
+          if (l <= lmax && c < a.ncomp) v = reinterpret_cast<const double2 *>(a.alm.p[c])[cbase + l];
+          s_alm[idx] = v;
+        }
+      } else {
+        for (int idx = threadIdx.x; idx < LCH * (NB / 2); idx += 128) {
+          const int li = idx / (NB / 2), f = idx - li * (NB / 2);
+          const int l = lc + li;
+          double2 E = make_double2(0., 0.), B = make_double2(0., 0.);
+          if (l <= lmax && 2 * f < a.ncomp) {
+            E = reinterpret_cast<const double2 *>(a.alm.p[2 * f])[cbase + l];
+            B = reinterpret_cast<const double2 *>(a.alm.p[2 * f + 1])[cbase + l];
+          }
+          // 2a = -(E + iB), -2a = -(E - iB)
+          s_alm[li * NB + 2 * f] = make_double2(-(E.x - B.y), -(E.y + B.x));
+          s_alm[li * NB + 2 * f + 1] = make_double2(-(E.x + B.y), -(E.y - B.x));
+        }
+      }
+      for (int i = threadIdx.x; i < LCH; i += 128) {
+        const int l = lc + i;
+        if (SPIN == 0) {
+          double2 cf = make_double2(0., 0.);
+          if (l < lmax) cf = __ldg(reinterpret_cast<const double2 *>(a.coef) + cbase + l);
+          reinterpret_cast<double2 *>(s_coef)[i] = cf;
+        } else {
+          double4 cf = make_double4(0., 0., 0., 0.);
+          if (l < lmax) cf = ldg_d4(reinterpret_cast<const double4 *>(a.coef) + cbase + l);
+          reinterpret_cast<double4 *>(s_coef)[i] = cf;
+        }
       }
       __syncthreads();
-      if (!alive) continue;
-      const int lend = min(LCH, lmax - lc + 1);
-      for (int li = 0; li < lend; ++li) {
-        const int l = lc + li;
-        const double sg = ((l + m) & 1) ? -1.0 : 1.0;
-        const double *al = s_alm + li * NB * 2;
-        if (SPIN == 0) {
-          if (sp.e == 0) {
-            const double lam = sp.cur, lams = sg * lam;
-#pragma unroll
-            for (int c = 0; c < NB; ++c) {
-              aN[c][0] = fma(lam, al[2 * c], aN[c][0]);
-              aN[c][1] = fma(lam, al[2 * c + 1], aN[c][1]);
-              aS[c][0] = fma(lams, al[2 * c], aS[c][0]);
-              aS[c][1] = fma(lams, al[2 * c + 1], aS[c][1]);
-            }
-          }
-          if (l < lmax) {
-            const double2 cf = __ldg(reinterpret_cast<const double2 *>(a.coef) + cbase + l);
+      if (!__any_sync(0xffffffffu, alive)) continue;
+      const bool scaled = __any_sync(0xffffffffu, sp.e < 0 || (SPIN != 0 && sm.e < 0));
+      const bool any_live = __any_sync(0xffffffffu, alive && (sp.e == 0 || (SPIN != 0 && sm.e == 0)));
+      if (!any_live) {
+        // nothing representable yet in this warp: advance the recursions only
+        for (int li = 0; li < LCH; ++li) {
+          if (SPIN == 0) {
+            const double2 cf = reinterpret_cast<const double2 *>(s_coef)[li];
             lam_advance(sp, cf.x * x, cf.y);
-          }
-        } else {
-          const double lp = (sp.e == 0) ? sp.cur : 0.0;
-          const double lm = (sm.e == 0) ? sm.cur : 0.0;
-          if (sp.e == 0 || sm.e == 0) {
-            // accumulate P = sum 2a lam+, M = sum -2a lam-  (north); south swaps lam+-
-#pragma unroll
-            for (int c = 0; c < NB; c += 2) {
-              const double Er = al[2 * c], Ei = al[2 * c + 1];
-              const double Br = al[2 * c + 2], Bi = al[2 * c + 3];
-              const double a2r = -(Er - Bi), a2i = -(Ei + Br);
-              const double m2r = -(Er + Bi), m2i = -(Ei - Br);
-              aN[c][0] = fma(lp, a2r, aN[c][0]);
-              aN[c][1] = fma(lp, a2i, aN[c][1]);
-              aN[c + 1][0] = fma(lm, m2r, aN[c + 1][0]);
-              aN[c + 1][1] = fma(lm, m2i, aN[c + 1][1]);
-              aS[c][0] = fma(sg * lm, a2r, aS[c][0]);
-              aS[c][1] = fma(sg * lm, a2i, aS[c][1]);
-              aS[c + 1][0] = fma(sg * lp, m2r, aS[c + 1][0]);
-              aS[c + 1][1] = fma(sg * lp, m2i, aS[c + 1][1]);
-            }
-          }
-          if (l < lmax) {
-            const double4 cf = ldg_d4(reinterpret_cast<const double4 *>(a.coef) + cbase + l);
+          } else {
+            const double4 cf = reinterpret_cast<const double4 *>(s_coef)[li];
             lam_advance(sp, fma(cf.x, x, cf.y), cf.z);
             lam_advance(sm, fma(cf.x, x, -cf.y), cf.z);
+          }
+        }
+        continue;
+      }
+#pragma unroll 2
+      for (int li = 0; li < LCH; li += 2) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const double2 *al = s_alm + (li + q) * NB;
+          if (SPIN == 0) {
+            const double2 cf = reinterpret_cast<const double2 *>(s_coef)[li + q];
+            const double lam = (!scaled || sp.e == 0) ? sp.cur : 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+              const double2 v = al[c];
+              acc[q][c][0] = fma(lam, v.x, acc[q][c][0]);
+              acc[q][c][1] = fma(lam, v.y, acc[q][c][1]);
+            }
+            if (scaled) {
+              lam_advance(sp, cf.x * x, cf.y);
+            } else {
+              const double nw = fma(cf.x * x, sp.cur, -(cf.y * sp.prev));
+              sp.prev = sp.cur;
+              sp.cur = nw;
+            }
+          } else {
+            const double4 cf = reinterpret_cast<const double4 *>(s_coef)[li + q];
+            const double lp = (!scaled || sp.e == 0) ? sp.cur : 0.0;
+            const double lm = (!scaled || sm.e == 0) ? sm.cur : 0.0;
+            // (-1)^(l+m): slot q = 0 has parity pb
+            const double sg = ((q + pb) & 1) ? -1.0 : 1.0;
+            const double slp = sg * lp, slm = sg * lm;
+#pragma unroll
+            for (int f = 0; f < NB / 2; ++f) {
+              const double2 a2 = al[2 * f], m2 = al[2 * f + 1];
+              acc[0][f][0] = fma(lp, a2.x, acc[0][f][0]);
+              acc[0][f][1] = fma(lp, a2.y, acc[0][f][1]);
+              acc[1][f][0] = fma(lm, m2.x, acc[1][f][0]);
+              acc[1][f][1] = fma(lm, m2.y, acc[1][f][1]);
+              // lambda^{+2}(pi - theta) = sg lambda^{-2}(theta) and vice versa
+              acc[2][f][0] = fma(slm, a2.x, acc[2][f][0]);
+              acc[2][f][1] = fma(slm, a2.y, acc[2][f][1]);
+              acc[3][f][0] = fma(slp, m2.x, acc[3][f][0]);
+              acc[3][f][1] = fma(slp, m2.y, acc[3][f][1]);
+            }
+            if (scaled) {
+              lam_advance(sp, fma(cf.x, x, cf.y), cf.z);
+              lam_advance(sm, fma(cf.x, x, -cf.y), cf.z);
+            } else {
+              const double np = fma(fma(cf.x, x, cf.y), sp.cur, -(cf.z * sp.prev));
+              const double nm = fma(fma(cf.x, x, -cf.y), sm.cur, -(cf.z * sm.prev));
+              sp.prev = sp.cur; sp.cur = np;
+              sm.prev = sm.cur; sm.cur = nm;
+            }
           }
         }
       }
     }
   }
   if (!valid) return;
-  for (int c = 0; c < NB && c < a.ncomp; ++c) {
-    double4 o;
-    if (SPIN == 0) {
-      o = make_double4(aN[c][0], aN[c][1], aS[c][0], aS[c][1]);
-    } else {
-      // c even: Q = (P + M)/2 ; c odd: U = (P - M)/(2i)
-      const int cq = c & ~1;
-      const double PrN = aN[cq][0], PiN = aN[cq][1], MrN = aN[cq + 1][0], MiN = aN[cq + 1][1];
-      const double PrS = aS[cq][0], PiS = aS[cq][1], MrS = aS[cq + 1][0], MiS = aS[cq + 1][1];
-      if ((c & 1) == 0)
-        o = make_double4(0.5 * (PrN + MrN), 0.5 * (PiN + MiN), 0.5 * (PrS + MrS), 0.5 * (PiS + MiS));
-      else
-        o = make_double4(0.5 * (PiN - MiN), -0.5 * (PrN - MrN), 0.5 * (PiS - MiS), -0.5 * (PrS - MrS));
+  double *dst = phase_out + ((i64)m * a.nrp_local + rp) * a.ncomp * 4;
+  if (SPIN == 0) {
+    // slot q = 0 holds the terms with (l+m) parity pb
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      if (c < a.ncomp) {
+        const double er = pb ? acc[1][c][0] : acc[0][c][0], ei = pb ? acc[1][c][1] : acc[0][c][1];
+        const double orr = pb ? acc[0][c][0] : acc[1][c][0], oi = pb ? acc[0][c][1] : acc[1][c][1];
+        *reinterpret_cast<double4 *>(dst + c * 4) = make_double4(er + orr, ei + oi, er - orr, ei - oi);
+      }
     }
-    *reinterpret_cast<double4 *>(phase_out + (((i64)m * a.nrp_local + rp) * a.ncomp + c) * 4) = o;
+  } else {
+#pragma unroll
+    for (int f = 0; f < NB / 2; ++f) {
+      if (2 * f < a.ncomp) {
+        const double PrN = acc[0][f][0], PiN = acc[0][f][1], MrN = acc[1][f][0], MiN = acc[1][f][1];
+        const double PrS = acc[2][f][0], PiS = acc[2][f][1], MrS = acc[3][f][0], MiS = acc[3][f][1];
+        // Q = (P + M)/2 ; U = (P - M)/(2i)
+        *reinterpret_cast<double4 *>(dst + (2 * f) * 4) =
+            make_double4(0.5 * (PrN + MrN), 0.5 * (PiN + MiN), 0.5 * (PrS + MrS), 0.5 * (PiS + MiS));
+        *reinterpret_cast<double4 *>(dst + (2 * f + 1) * 4) =
+            make_double4(0.5 * (PiN - MiN), -0.5 * (PrN - MrN), 0.5 * (PiS - MiS), -0.5 * (PrS - MrS));
+      }
+    }
   }
 }
 
@@ -185,7 +241,8 @@ int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c) {
   HCU_CUDA(cudaMalloc(&c->tab, sizeof(double) * per * nalm));
   coef_kernel<<<c->lmax + 1, 128, 0, ctx->stream>>>(c->lmax, c->spin, c->tab);
   HCU_LAUNCH_CHECK(ctx);
-  // start-value normalisation in long double on the host
+  // start-value normalisation in long double on the host:
+  //   cm[2m] = c_m with lambda_mm = (-1)^m c_m sin^m(theta);  cm[2m+1] = c_m sqrt(m(m-1)/((m+1)(m+2)))
   std::vector<double> cm(2 * (size_t)(c->lmax + 1));
   long double v = sqrtl(1.0L / (4.0L * 3.141592653589793238462643383279502884L));
   for (int m = 0; m <= c->lmax; ++m) {
@@ -202,9 +259,9 @@ int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c) {
   return HCU_OK;
 }
 
-
 int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
                            int spin, int ncomp, const hcu_ptrs &alm, double *phase) {
+  HCU_ARG(ncomp >= 1 && ncomp <= HCU_MAX_BATCH, "synthesis batch size");
   LegArgs a;
   a.lmax = lmax;
   a.nm = lmax + 1;
@@ -229,7 +286,6 @@ int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
     if (ncomp <= 6) return launch_synthesis<0, 6>(ctx, a, phase);
     if (ncomp <= 8) return launch_synthesis<0, 8>(ctx, a, phase);
     if (ncomp <= 10) return launch_synthesis<0, 10>(ctx, a, phase);
-    HCU_ARG(ncomp <= 12, "synthesis batch size");
     return launch_synthesis<0, 12>(ctx, a, phase);
   } else {
     if (ncomp <= 2) return launch_synthesis<2, 2>(ctx, a, phase);
@@ -237,7 +293,6 @@ int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
     if (ncomp <= 6) return launch_synthesis<2, 6>(ctx, a, phase);
     if (ncomp <= 8) return launch_synthesis<2, 8>(ctx, a, phase);
     if (ncomp <= 10) return launch_synthesis<2, 10>(ctx, a, phase);
-    HCU_ARG(ncomp <= 12, "synthesis batch size");
     return launch_synthesis<2, 12>(ctx, a, phase);
   }
 }

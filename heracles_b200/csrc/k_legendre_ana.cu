@@ -52,11 +52,12 @@ struct Cfg {
   static constexpr int F_WARP = 32 * F_ROW;
   static constexpr int WARP_SMEM = LAM_WARP + F_WARP;
   static constexpr int NOUT = 2 * LP * C;
+  static constexpr int OS = LC + 2;               // column stride of the staged out tile
   static constexpr int COEF_W = SPIN == 0 ? 2 : 4;  // doubles per coefficient entry
   static constexpr int COEF_OFF = 8 * WARP_SMEM;
   static constexpr int FLAG_OFF = COEF_OFF + LC * COEF_W;
   static constexpr size_t SMEM_BYTES = (size_t)(FLAG_OFF + 8) * 8;
-  static_assert(NOUT <= LAM_WARP, "out tile must fit in the lambda tile");
+  static_assert(C * OS <= LAM_WARP, "out tile must fit in the lambda tile");
 };
 
 template <int SPIN, int NBLK>
@@ -267,15 +268,19 @@ __global__ void __launch_bounds__(256, 1) legendre_analysis_kernel(LegArgs a) {
       }
       n_acc += 1;
       __syncwarp();
-      // this warp's partial tile over its (now consumed) lambda tile: out_w[(p*LP + lidx)*C + col]
+      // this warp's partial tile over its (now consumed) lambda tile, column major
+      // with stride LC + 2 (conflict free for these stores and for the flush loads):
+      //   out_w[col * (LC + 2) + p * LP + lidx]
 #pragma unroll
       for (int p = 0; p < 2; ++p)
 #pragma unroll
         for (int mb = 0; mb < K::MB; ++mb)
 #pragma unroll
-          for (int nb = 0; nb < NBLK; ++nb)
-            *reinterpret_cast<double2 *>(lam_w + (p * K::LP + mb * 8 + fb) * K::C + nb * 8 + 2 * fa) =
-                make_double2(acc[p][mb][nb][0], acc[p][mb][nb][1]);
+          for (int nb = 0; nb < NBLK; ++nb) {
+            double *o = lam_w + (nb * 8 + 2 * fa) * K::OS + p * K::LP + mb * 8 + fb;
+            o[0] = acc[p][mb][nb][0];
+            o[K::OS] = acc[p][mb][nb][1];
+          }
     }
     if (lane == 0) flags[warp] = live ? 1 : 0;
     __syncthreads();
@@ -286,10 +291,10 @@ __global__ void __launch_bounds__(256, 1) legendre_analysis_kernel(LegArgs a) {
       for (int w = 0; w < 8; ++w) fl_any |= flags[w];
       if (fl_any) {
         for (int o = threadIdx.x; o < K::NOUT; o += 256) {
-          // o = col * LC + s  (consecutive threads -> consecutive l -> consecutive alm addresses)
-          const int col = o / K::LC, s = o - col * K::LC;
-          const int l = lstart + s;
-          const int p = (s + pb) & 1, lidx = s >> 1;
+          // o = col * LC + (p * LP + lidx): consecutive threads read consecutive doubles
+          const int col = o / K::LC, t = o - col * K::LC;
+          const int p = t / K::LP, lidx = t - p * K::LP;
+          const int l = lstart + 2 * lidx + ((p - pb) & 1);
           int row, ri;
           if (SPIN == 0) {
             row = col >> 1;
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(256, 1) legendre_analysis_kernel(LegArgs a) {
             double sum = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; ++w)
-              if (flags[w]) sum += smem_d[w * K::WARP_SMEM + (p * K::LP + lidx) * K::C + col];
+              if (flags[w]) sum += smem_d[w * K::WARP_SMEM + col * K::OS + t];
             if (a.fl) sum *= a.fl[l];
             atomicAdd(a.alm.p[row] + 2 * (cbase + l) + ri, sum);
           }

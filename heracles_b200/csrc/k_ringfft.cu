@@ -259,22 +259,52 @@ __global__ void belt_pre_inv_kernel(i64 nside, int lmax, int ncomp, int comp,
 // Z is the spectrum of z_j = fN_j + i fS_j: z_j = sum_k Z[k] e^{+2 pi i jk/n}.
 // With j = 4 j' + q:  z_{4j'+q} = sum_{k'=0}^{i-1} e^{2 pi i j'k'/i}
 //      [ e^{2 pi i q k'/n} sum_{s=0}^{3} Z[k' + s i] e^{2 pi i q s/4} ].
-__global__ void cap_fft_inv_kernel(int ilo, int M, i64 nside, int lmax, int ncomp,
-                                   int comp, const double *phase,
+// Step 1 (cap_pre_inv_kernel): fold the m <= lmax coefficients of one ring pair
+// onto the 4i frequencies, Z[k] = GN[k] + i GS[k]; grid (k blocks, cap ring pairs, comps).
+__global__ void cap_pre_inv_kernel(i64 nside, int lmax, int ncomp, const double *phase,
+                                   double2 *Z, i64 ncap) {
+  const int i = blockIdx.y + 1;
+  const int n = 4 * i;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int comp = blockIdx.z;
+  const i64 nrp = 2 * nside;
+  const i64 rp = i - 1;
+  // G[k] folded from m = k (mod n) and, conjugated, from m = -k (mod n)
+  double2 gn = make_double2(0., 0.), gs = make_double2(0., 0.);
+  for (int m = k; m <= lmax; m += n) {
+    const double4 p = *reinterpret_cast<const double4 *>(phase + (((i64)m * nrp + rp) * ncomp + comp) * 4);
+    double2 e = expmipi((double)m / (4.0 * (double)i));
+    gn = cadd(gn, cmulc(make_double2(p.x, p.y), e));
+    gs = cadd(gs, cmulc(make_double2(p.z, p.w), e));
+  }
+  for (int m = n - k; m <= lmax; m += n) {
+    if (m == 0) continue;
+    const double4 p = *reinterpret_cast<const double4 *>(phase + (((i64)m * nrp + rp) * ncomp + comp) * 4);
+    double2 e = expmipi((double)m / (4.0 * (double)i));
+    double2 cn = cmulc(make_double2(p.x, p.y), e);
+    double2 cs = cmulc(make_double2(p.z, p.w), e);
+    gn = cadd(gn, make_double2(cn.x, -cn.y));
+    gs = cadd(gs, make_double2(cs.x, -cs.y));
+  }
+  Z[(i64)comp * ncap + 2LL * i * (i - 1) + k] = make_double2(gn.x - gs.y, gn.y + gs.x);
+}
+
+// Step 2: four decimated inverse sub-FFTs per ring pair; grid (rings of one size class, comps)
+__global__ void cap_fft_inv_kernel(int ilo, int M, i64 nside, const double2 *Z, i64 ncap,
                                    const double2 *bfilt, const i64 *off,
                                    hcu_ptrs maps) {
   extern __shared__ double2 smem[];
   double2 *a = smem;
   double2 *tw = smem + M;
   const int i = ilo + blockIdx.x;
-  const int n = 4 * i;
+  const int comp = blockIdx.y;
   const i64 npix = 12 * nside * nside;
-  const i64 nrp = 2 * nside;
-  const i64 rp = i - 1;
   const i64 startN = 2LL * i * (i - 1);
   const i64 startS = npix - startN - 4LL * i;
   double *mN = maps.p[comp] + startN;
   double *mS = maps.p[comp] + startS;
+  const double2 *Zr = Z + (i64)comp * ncap + startN;
   const double2 *B = bfilt + off[i];
   make_twiddles(tw, M);
   __syncthreads();
@@ -285,25 +315,7 @@ __global__ void cap_fft_inv_kernel(int ilo, int M, i64 nside, int lmax, int ncom
       if (kp < i) {
         double2 acc = make_double2(0., 0.);
         for (int s = 0; s < 4; ++s) {
-          int k = kp + s * i;
-          // Z[k] = GN[k] + i GS[k], G[k] folded from m = k mod n and m = -k mod n
-          double2 gn = make_double2(0., 0.), gs = make_double2(0., 0.);
-          for (int m = k; m <= lmax; m += n) {
-            const double *p = phase + (((i64)m * nrp + rp) * ncomp + comp) * 4;
-            double2 e = expmipi((double)m / (4.0 * (double)i));
-            gn = cadd(gn, cmulc(make_double2(p[0], p[1]), e));
-            gs = cadd(gs, cmulc(make_double2(p[2], p[3]), e));
-          }
-          for (int m = n - k; m <= lmax; m += n) {
-            if (m == 0) continue;
-            const double *p = phase + (((i64)m * nrp + rp) * ncomp + comp) * 4;
-            double2 e = expmipi((double)m / (4.0 * (double)i));
-            double2 cn = cmulc(make_double2(p[0], p[1]), e);
-            double2 cs = cmulc(make_double2(p[2], p[3]), e);
-            gn = cadd(gn, make_double2(cn.x, -cn.y));
-            gs = cadd(gs, make_double2(cs.x, -cs.y));
-          }
-          double2 z = make_double2(gn.x - gs.y, gn.y + gs.x);
+          const double2 z = Zr[kp + s * i];
           // e^{2 pi i q s / 4}
           int r = (q * s) & 3;
           double2 zr = (r == 0) ? z
@@ -471,7 +483,12 @@ int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
   const int n4 = (int)(4 * nside);
   const int nk = n4 / 2 + 1;
   // caps
-  for (int c = 0; c < ncomp; ++c) {
+  if (nside > 1) {
+    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_cap, sizeof(double2) * (size_t)ncap * ncomp));
+    double2 *Z = (double2 *)ctx->ws_cap.ptr;
+    dim3 pgrid((unsigned)((4 * (nside - 1) + 127) / 128), (unsigned)(nside - 1), (unsigned)ncomp);
+    cap_pre_inv_kernel<<<pgrid, 128, 0, ctx->stream>>>(nside, lmax, ncomp, phase, Z, ncap);
+    HCU_LAUNCH_CHECK(ctx);
     int i = 1;
     while (i < nside) {
       int M = bluestein_M(i);
@@ -480,8 +497,9 @@ int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
       size_t smem = (size_t)M * 24;
       HCU_CUDA(cudaFuncSetAttribute(cap_fft_inv_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      cap_fft_inv_kernel<<<ihi - i + 1, cap_threads(M), smem, ctx->stream>>>(
-          i, M, nside, lmax, ncomp, c, phase, g->bfilt, g->bfilt_off, maps);
+      dim3 grid(ihi - i + 1, ncomp);
+      cap_fft_inv_kernel<<<grid, cap_threads(M), smem, ctx->stream>>>(
+          i, M, nside, Z, ncap, g->bfilt, g->bfilt_off, maps);
       HCU_LAUNCH_CHECK(ctx);
       i = ihi + 1;
     }
