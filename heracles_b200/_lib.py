@@ -13,7 +13,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libheracles_cuda.so")
+# HERACLES_CUDA_LIB points at an alternative build of the SAME library (kernel tuning experiments)
+LIB_PATH = os.environ.get("HERACLES_CUDA_LIB") or os.path.join(_HERE, "lib", "libheracles_cuda.so")
 
 c_int = ctypes.c_int
 c_i64 = ctypes.c_int64

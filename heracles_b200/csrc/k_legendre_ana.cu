@@ -27,6 +27,10 @@
 // by the batch; accumulate 4 flop per spin-0 map, 16 per spin-2 field.
 #include "legendre_common.cuh"
 
+#ifndef HCU_ANA_WARPS
+#define HCU_ANA_WARPS 8
+#endif
+
 namespace {
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
@@ -54,14 +58,16 @@ struct Cfg {
   static constexpr int NOUT = 2 * LP * C;
   static constexpr int OS = LC + 2;               // column stride of the staged out tile
   static constexpr int COEF_W = SPIN == 0 ? 2 : 4;  // doubles per coefficient entry
-  static constexpr int COEF_OFF = 8 * WARP_SMEM;
+  static constexpr int NW = HCU_ANA_WARPS;          // warps per CTA, 32 ring pairs each
+  static constexpr int NT = 32 * NW;
+  static constexpr int COEF_OFF = NW * WARP_SMEM;
   static constexpr int FLAG_OFF = COEF_OFF + LC * COEF_W;
   static constexpr size_t SMEM_BYTES = (size_t)(FLAG_OFF + 8) * 8;
   static_assert(C * OS <= LAM_WARP, "out tile must fit in the lambda tile");
 };
 
 template <int SPIN, int NBLK>
-__global__ void __launch_bounds__(256, 1) legendre_analysis_kernel(LegArgs a) {
+__global__ void __launch_bounds__(32 * HCU_ANA_WARPS, HCU_ANA_WARPS == 8 ? 1 : 2) legendre_analysis_kernel(LegArgs a) {
   using K = Cfg<SPIN, NBLK>;
   extern __shared__ __align__(16) double smem_d[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -70,7 +76,7 @@ __global__ void __launch_bounds__(256, 1) legendre_analysis_kernel(LegArgs a) {
   double *coef_s = smem_d + K::COEF_OFF;
   int *flags = reinterpret_cast<int *>(smem_d + K::FLAG_OFF);
 
-  const int ngroups = (int)((a.nrp_local + 255) / 256);
+  const int ngroups = (int)((a.nrp_local + K::NT - 1) / K::NT);
   const int g = blockIdx.x % ngroups;
   const int mi = blockIdx.x / ngroups;
   const int m = a.mlist ? a.mlist[mi] : mi;
@@ -79,7 +85,7 @@ __global__ void __launch_bounds__(256, 1) legendre_analysis_kernel(LegArgs a) {
   if (l0 > lmax) return;
   const int pb = (l0 + m) & 1;
 
-  const i64 rpl = (i64)g * 256 + warp * 32 + lane;
+  const i64 rpl = (i64)g * K::NT + warp * 32 + lane;
   const bool valid = rpl < a.nrp_local;
   double x = 0, sth = 1, chh = 1, shh = 1;
   if (valid) {
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(256, 1) legendre_analysis_kernel(LegArgs a) {
   // coefficients of chunk `chk` -> shared (entry i belongs to l = lstart + i; zero past lmax)
   auto stage_coef = [&](int chk) {
     const int lstart = l0 + chk * K::LC;
-    for (int i = threadIdx.x; i < K::LC; i += 256) {
+    for (int i = threadIdx.x; i < K::LC; i += K::NT) {
       const int l = lstart + i;
       if (SPIN == 0) {
         double2 cf = make_double2(0., 0.);
@@ -115,7 +121,7 @@ __global__ void __launch_bounds__(256, 1) legendre_analysis_kernel(LegArgs a) {
 
   // ---- stage F (ring Fourier coefficients of this m) into shared memory ----
   {
-    const i64 row0 = (i64)g * 256 + warp * 32;
+    const i64 row0 = (i64)g * K::NT + warp * 32;
     const double *src = a.phase + ((i64)mi * a.nrp_local + row0) * a.ncomp * 4;
     const int rows = (int)max((i64)0, min((i64)32, a.nrp_local - row0));
     const int w = a.ncomp * 4;
@@ -288,9 +294,9 @@ __global__ void __launch_bounds__(256, 1) legendre_analysis_kernel(LegArgs a) {
     {
       int fl_any = 0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) fl_any |= flags[w];
+      for (int w = 0; w < K::NW; ++w) fl_any |= flags[w];
       if (fl_any) {
-        for (int o = threadIdx.x; o < K::NOUT; o += 256) {
+        for (int o = threadIdx.x; o < K::NOUT; o += K::NT) {
           // o = col * LC + (p * LP + lidx): consecutive threads read consecutive doubles
           const int col = o / K::LC, t = o - col * K::LC;
           const int p = t / K::LP, lidx = t - p * K::LP;
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(256, 1) legendre_analysis_kernel(LegArgs a) {
           if (l <= lmax && row < a.ncomp) {
             double sum = 0.0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w)
+            for (int w = 0; w < K::NW; ++w)
               if (flags[w]) sum += smem_d[w * K::WARP_SMEM + col * K::OS + t];
             if (a.fl) sum *= a.fl[l];
             atomicAdd(a.alm.p[row] + 2 * (cbase + l) + ri, sum);
@@ -327,13 +333,13 @@ __global__ void __launch_bounds__(256, 1) legendre_analysis_kernel(LegArgs a) {
 template <int SPIN, int NBLK>
 int launch_analysis(hcu_ctx *ctx, const LegArgs &a) {
   using K = Cfg<SPIN, NBLK>;
-  const int ngroups = (int)((a.nrp_local + 255) / 256);
+  const int ngroups = (int)((a.nrp_local + K::NT - 1) / K::NT);
   const i64 nblocks = (i64)ngroups * a.nm;
   if (nblocks <= 0) return HCU_OK;
   HCU_CUDA(cudaFuncSetAttribute(legendre_analysis_kernel<SPIN, NBLK>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)K::SMEM_BYTES));
-  legendre_analysis_kernel<SPIN, NBLK><<<(unsigned)nblocks, 256, K::SMEM_BYTES, ctx->stream>>>(a);
+  legendre_analysis_kernel<SPIN, NBLK><<<(unsigned)nblocks, K::NT, K::SMEM_BYTES, ctx->stream>>>(a);
   HCU_LAUNCH_CHECK(ctx);
   return HCU_OK;
 }
