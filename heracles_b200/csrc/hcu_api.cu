@@ -107,6 +107,7 @@ extern "C" int hcu_destroy(hcu_ctx *ctx) {
   }
   for (auto &kv : ctx->coef) {
     cudaFree(kv.second.tab);
+    cudaFree(kv.second.scale);
     cudaFree(kv.second.cm);
   }
   for (auto &kv : ctx->belt_plan) cufftDestroy(kv.second);

@@ -85,8 +85,9 @@ struct hcu_geom {
 // per-(lmax, spin) recursion coefficient table
 struct hcu_coef {
   int lmax = 0, spin = 0;
-  double *tab = nullptr; // spin 0: double2 (alpha, gamma); spin 2: double4 (alpha, alpha*beta, gamma, 0)
-  double *cm = nullptr;  // [lmax+1] start-value normalisation (mantissa), see k_legendre.cu
+  double *tab = nullptr;   // scaled recursion: spin 0 double A_l; spin 2 double2 (A_l, B_l); see k_legendre.cu
+  double *scale = nullptr; // s_l with lambda_l = s_l q_l
+  double *cm = nullptr;    // [2 (lmax+1)] start-value normalisation
 };
 
 struct hcu_stage_slot {
@@ -137,12 +138,15 @@ int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
 int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
                          const double *phase, const hcu_ptrs &maps);
 int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c);
+int hcu_legendre_batch(int spin);  // components one Legendre launch can take: 12 (spin 0), 8 (spin 2)
 int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
                           int spin, int ncomp, const double *phase,
                           const int32_t *mlist_dev, int nm, i64 rp_lo, i64 rp_hi,
                           const double *fl_dev, const hcu_ptrs &alm);
 int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
-                           int spin, int ncomp, const hcu_ptrs &alm, double *phase);
+                           int spin, int ncomp, const hcu_ptrs &alm,
+                           const int32_t *mlist_dev, int nm, i64 rp_lo, i64 rp_hi,
+                           double *phase);
 
 static inline int ilog2_host(i64 v) {
   int r = 0;

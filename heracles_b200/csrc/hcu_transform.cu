@@ -87,8 +87,9 @@ int analysis_pass(hcu_ctx *ctx, hcu_geom *g, hcu_coef *cf, int lmax, int spin, i
   const i64 nside = g->nside;
   const i64 npix = 12 * nside * nside;
   const i64 nrp = g->nrp;
-  for (int c0 = 0; c0 < nmaps; c0 += HCU_MAX_BATCH) {
-    const int nb = std::min(HCU_MAX_BATCH, nmaps - c0);
+  const int cap = hcu_legendre_batch(spin);
+  for (int c0 = 0; c0 < nmaps; c0 += cap) {
+    const int nb = std::min(cap, nmaps - c0);
     hcu_ptrs src, dst;
     for (int c = 0; c < HCU_MAX_BATCH; ++c) {
       src.p[c] = c < nb ? maps[c0 + c] : nullptr;
@@ -120,8 +121,9 @@ int analysis_pass(hcu_ctx *ctx, hcu_geom *g, hcu_coef *cf, int lmax, int spin, i
 int synthesis_pass(hcu_ctx *ctx, hcu_geom *g, hcu_coef *cf, int lmax, int spin, int nmaps,
                    double *const *alm, double *const *maps) {
   const i64 nrp = g->nrp;
-  for (int c0 = 0; c0 < nmaps; c0 += HCU_MAX_BATCH) {
-    const int nb = std::min(HCU_MAX_BATCH, nmaps - c0);
+  const int cap = hcu_legendre_batch(spin);
+  for (int c0 = 0; c0 < nmaps; c0 += cap) {
+    const int nb = std::min(cap, nmaps - c0);
     hcu_ptrs src, dst;
     for (int c = 0; c < HCU_MAX_BATCH; ++c) {
       src.p[c] = c < nb ? alm[c0 + c] : nullptr;
@@ -130,7 +132,7 @@ int synthesis_pass(hcu_ctx *ctx, hcu_geom *g, hcu_coef *cf, int lmax, int spin, 
     HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_phase, sizeof(double) * 4 * (size_t)(lmax + 1) * nrp * nb));
     double *phase = (double *)ctx->ws_phase.ptr;
     StageTimer t0(ctx, 0, &ctx->sht_ms[2]);
-    HCU_CHECK(hcu_legendre_synthesis(ctx, g, cf, lmax, spin, nb, src, phase));
+    HCU_CHECK(hcu_legendre_synthesis(ctx, g, cf, lmax, spin, nb, src, nullptr, lmax + 1, 0, nrp, phase));
     t0.stop();
     StageTimer t1(ctx, 2, &ctx->sht_ms[3]);
     HCU_CHECK(hcu_ring_fft_inverse(ctx, g, lmax, nb, phase, dst));
@@ -197,7 +199,7 @@ extern "C" int hcu_map2alm_many(hcu_ctx *ctx, int64_t nside, int lmax, int spin,
                          niter == 0 ? dfl : nullptr, dalm.data());
   if (rc == HCU_OK && niter > 0) {
     // Jacobi refinement in batches so the residual buffer stays small
-    const int cap = HCU_MAX_BATCH;
+    const int cap = hcu_legendre_batch(spin);
     rc = hcu_ws_reserve(ctx, &resid, sizeof(double) * npix * std::min(cap, nmaps));
     for (int c0 = 0; c0 < nmaps && rc == HCU_OK; c0 += cap) {
       const int nb = std::min(cap, nmaps - c0);
@@ -316,7 +318,7 @@ extern "C" int hcu_phase2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, in
                              int64_t alm_stride) {
   HCU_CHECK(check_sht_args(ctx, nside, lmax, spin, ncomp));
   HCU_ARG(phase && alm && nm >= 0, "null pointer");
-  HCU_ARG(ncomp <= HCU_MAX_BATCH, "at most 10 components per call");
+  HCU_ARG(ncomp <= hcu_legendre_batch(spin), "at most 12 (spin 0) / 8 (spin 2) components per call");
   HCU_ARG(0 <= rp_lo && rp_lo <= rp_hi && rp_hi <= 2 * nside, "ring pair range");
   HCU_ARG(hcu_dev_accessible(phase) && hcu_dev_accessible(alm), "device pointers required");
   HCU_ARG(!mlist || hcu_dev_accessible(mlist), "mlist must be on the device");

@@ -1,245 +1,681 @@
-// k_legendre.cu -- FP64 Legendre stage of the spherical-harmonic SYNTHESIS
-// (alm -> ring Fourier coefficients) on HEALPix ring pairs, spin 0 and spin 2,
-// batched over up to 12 components; plus the recursion coefficient tables
-// shared with the analysis kernel (k_legendre_ana.cu).
+// k_legendre.cu -- FP64 Legendre stage of the spherical-harmonic transform on HEALPix
+// ring pairs: ANALYSIS (ring Fourier coefficients -> alm) and SYNTHESIS (alm -> ring
+// Fourier coefficients), spin 0 and spin 2, batched over up to 12 (spin 0) / 8 (spin 2)
+// components.
 //
-// Replaces the libsharp/ducc Legendre loop behind hp.alm2map, which healpy's
-// map2alm runs inside its default iter=3 refinement (heracles/healpy.py:183-189).
-// FP64 FMA bound.
+// Replaces the libsharp/ducc Legendre loops behind hp.map2alm and (inside its default
+// iter=3 refinement) hp.alm2map -- heracles/healpy.py:183-189.  Bound: the FP64 pipe
+// (DMMA 37.1 TFLOP/s, DFMA 36.0, ONE shared pipe; tools/dmma_peak.cu).
 //
-// One lane = one ring pair: it advances its own lambda_lm(theta) recursion in l
-// and accumulates  b_m(theta) = sum_l a_lm lambda_lm(theta)  for every component
-// of the batch in registers, so there is no cross-lane reduction.  The a_lm and
-// the recursion coefficients of a chunk of l are staged once per CTA in shared
-// memory and read as warp-wide broadcasts.  North and south rings share the
-// recursion through lambda_lm(pi - theta) = (-1)^(l+m) lambda_lm(theta): spin 0
-// keeps separate even / odd (l+m) accumulators and forms N = E + O, S = E - O at
-// the end, which halves the FMAs.
+// One CTA = one m and 256 ring pairs; 8 warps; one warp = 32 ring pairs and does BOTH
+// jobs for them, software pipelined in sub-chunks of 16 l:
+//   recursion  one ring pair per lane: q_{l+1} = (A_l x +- B_l) q_l - q_{l-1} with
+//       lambda_l = s_l q_l (two FMAs per step; the s_l are folded into the outputs resp.
+//       the staged a_lm), extended-exponent rescaling while the value is below 2^-200.
+//       The 16 values of sub-chunk i+1 go to the warp's second shared-memory tile
+//       Lam[j][parity][ring][8] (j: spin 2 has lambda^+2 and lambda^-2), XOR-swizzled so
+//       that these 128-bit stores and both kinds of fragment loads are conflict free,
+//   tensor ops  while the DMMAs (mma.sync.m8n8k4.f64) of sub-chunk i read the first tile:
+//         analysis   out[l][col] += sum_ring Lam[l][ring] B[ring][col]; the B fragments
+//                    (ring Fourier coefficients of the warp's 32 rings, all columns, both
+//                    parities) stay in REGISTERS for the whole CTA; per chunk of 32 l the
+//                    eight warps' partial tiles are reduced through a double-buffered
+//                    shared tile (one CTA barrier per chunk) and added to alm with one
+//                    RED.ADD.F64 per output (x s_l x fl[l]).
+//         synthesis  G[ring][col] += sum_l Lam[ring][l] (s_l a_lm)[l][col]; accumulators
+//                    stay in registers for the whole CTA, the a_lm chunk is prefetched a
+//                    chunk ahead into a warp-private shared tile; no CTA barrier at all.
+// The recursion and the DMMAs are written into ONE instruction stream on purpose: a DFMA
+// chain in a warp of its own is starved by the scheduler as soon as two other warps of the
+// same SM sub-partition keep the FP64 pipe full of DMMAs (tools/mix_peak.cu: 17 000 clk per
+// dependent step), while DFMAs interleaved with the DMMAs of the same warp are free.
+//
+// Work per (l, m, ring pair): recursion 2 (spin 0) / 4 (spin 2) FP64 ops shared by the
+// batch; accumulate 4 flop per spin-0 map, 16 per spin-2 field (SURVEY 8(d) counts the
+// recursion as 4 / 12 flop, which is what the reported flop numbers use).
 #include "legendre_common.cuh"
 
 namespace {
 
-// phase out: [(m * nrp + rp) * ncomp + c] * 4 = (reN, imN, reS, imS)
-template <int SPIN, int NB>
-__global__ void __launch_bounds__(128) legendre_synthesis_kernel(LegArgs a, double *phase_out) {
-  constexpr int LCH = 32;                     // l per staged chunk (even)
-  constexpr int CW = SPIN == 0 ? 2 : 4;       // doubles per coefficient entry
-  __shared__ __align__(16) double2 s_alm[LCH * NB];
-  __shared__ __align__(16) double s_coef[LCH * CW];
-  const int ngroups = (int)((a.nrp_local + 127) / 128);
-  const int g = blockIdx.x % ngroups;
-  const int m = blockIdx.x / ngroups;
-  const int lmax = a.lmax;
-  const int l0 = (SPIN == 0) ? m : (m > 2 ? m : 2);
-  const i64 rp = (i64)g * 128 + threadIdx.x;
-  const bool valid = rp < a.nrp_local;
-  double x = 0, sth = 1, chh = 1, shh = 1;
-  if (valid) {
-    x = a.cth[rp];
+constexpr int NW = 8;        // warps per CTA
+constexpr int R = 32 * NW;   // ring pairs per CTA
+constexpr int SL = 16;       // l per sub-chunk (8 per parity = one m8 block)
+constexpr int LC = 32;       // l per chunk (flush / a_lm staging granularity)
+constexpr int NT = 32 * NW;
+constexpr int FLS = 34;      // column stride of a flush tile (32 l + 2: conflict free)
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Lam tile of one (j, parity): [ring 0..31][8 l], 16-byte units XOR-swizzled by the ring
+__device__ __forceinline__ int swzf(int ring) { return (((ring >> 1) & 1) << 1) | ((ring >> 2) & 1); }
+__device__ __forceinline__ int lam_off(int ring, int idx) {  // idx = l index within the parity, 0..7
+  return ring * 8 + 2 * ((idx >> 1) ^ swzf(ring)) + (idx & 1);
+}
+
+__device__ __forceinline__ double mask_d(double v, unsigned long long msk) {
+  return __longlong_as_double((long long)((unsigned long long)__double_as_longlong(v) & msk));
+}
+__device__ __forceinline__ double neg_d(double v) {  // sign flip on the integer pipe
+  return __longlong_as_double(__double_as_longlong(v) ^ (long long)0x8000000000000000ull);
+}
+
+template <int SPIN>
+struct Rec {
+  static constexpr int NJ = SPIN == 0 ? 1 : 2;
+  static constexpr int TILE = NJ * 2 * 256;  // doubles of one sub-chunk tile of a warp
+  LamState sp, sm;
+  double x;
+  unsigned long long mp, mm;  // store masks: all ones when the value is representable (e == 0)
+  bool alive;
+
+  __device__ __forceinline__ void begin_sub() {
+    mp = (sp.e == 0) ? ~0ull : 0ull;
+    mm = (sm.e == 0) ? ~0ull : 0ull;
+  }
+  // is anything of the sub-chunk about to be produced representable in this warp?
+  __device__ __forceinline__ bool sub_live() const {
+    return __any_sync(0xffffffffu, alive && (sp.e == 0 || (SPIN != 0 && sm.e == 0)));
+  }
+  // four recursion steps s..s+3 of the current sub-chunk (s multiple of 4) and their stores
+  __device__ __forceinline__ void step4(double *tile, const double *cf, int ring, int pb, int s) {
+    double vp[4], vm[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double2 c2 = reinterpret_cast<const double2 *>(cf)[s + u];
+      vp[u] = mask_d(sp.cur, mp);
+      if (SPIN == 0) {
+        const double nw = fma(c2.x * x, sp.cur, -sp.prev);
+        sp.prev = sp.cur;
+        sp.cur = nw;
+      } else {
+        vm[u] = mask_d(sm.cur, mm);
+        const double ap = fma(c2.x, x, c2.y), am = fma(c2.x, x, -c2.y);
+        const double np = fma(ap, sp.cur, -sp.prev);
+        const double nm = fma(am, sm.cur, -sm.prev);
+        sp.prev = sp.cur; sp.cur = np;
+        sm.prev = sm.cur; sm.cur = nm;
+      }
+    }
+    // steps s, s+2 have parity pb; s+1, s+3 parity 1-pb; l index within the parity s/2, s/2+1
+    const int o = ring * 8 + 2 * ((s >> 2) ^ swzf(ring));
+    *reinterpret_cast<double2 *>(tile + pb * 256 + o) = make_double2(vp[0], vp[2]);
+    *reinterpret_cast<double2 *>(tile + (1 - pb) * 256 + o) = make_double2(vp[1], vp[3]);
+    if (SPIN != 0) {
+      *reinterpret_cast<double2 *>(tile + (2 + pb) * 256 + o) = make_double2(vm[0], vm[2]);
+      *reinterpret_cast<double2 *>(tile + (3 - pb) * 256 + o) = make_double2(vm[1], vm[3]);
+    }
+  }
+  // extended-exponent bookkeeping, once per sub-chunk (values grow by far less than 2^400 in 16 steps)
+  __device__ __forceinline__ void end_sub() {
+    if (__any_sync(0xffffffffu, sp.e < 0 || (SPIN != 0 && sm.e < 0))) {
+      if (sp.e < 0 && fmax(fabs(sp.cur), fabs(sp.prev)) >= TWO_P200) {
+        sp.cur *= TWO_M400;
+        sp.prev *= TWO_M400;
+        sp.e += SCALE_STEP;
+      }
+      if (SPIN != 0 && sm.e < 0 && fmax(fabs(sm.cur), fabs(sm.prev)) >= TWO_P200) {
+        sm.cur *= TWO_M400;
+        sm.prev *= TWO_M400;
+        sm.e += SCALE_STEP;
+      }
+    }
+  }
+};
+
+// lanes 0..15 fetch the recursion coefficients of the 16 steps starting at l = lsub
+template <int SPIN>
+__device__ __forceinline__ void stage_coef(double *cf, const LegArgs &a, i64 cbase, int lsub, int lane) {
+  if (lane < SL) {
+    double2 c2 = make_double2(0., 0.);
+    const int l = lsub + lane;
+    if (l < a.lmax) {
+      if (SPIN == 0)
+        c2.x = __ldg(a.coef + cbase + l);
+      else
+        c2 = __ldg(reinterpret_cast<const double2 *>(a.coef) + cbase + l);
+    }
+    reinterpret_cast<double2 *>(cf)[lane] = c2;
+  }
+}
+
+struct Setup {
+  int g, mi, m, l0, pb, nrows, nchunk;
+  i64 row0, cbase;
+};
+
+template <int SPIN>
+__device__ __forceinline__ bool setup_cta(const LegArgs &a, Setup &s, Rec<SPIN> &rec, int warp, int lane) {
+  const int ngroups = (int)((a.nrp_local + R - 1) / R);
+  s.g = blockIdx.x % ngroups;
+  s.mi = blockIdx.x / ngroups;
+  s.m = a.mlist ? a.mlist[s.mi] : s.mi;
+  s.l0 = (SPIN == 0) ? s.m : (s.m > 2 ? s.m : 2);
+  s.row0 = (i64)s.g * R;
+  s.nrows = (int)min((i64)R, a.nrp_local - s.row0);
+  s.pb = (s.l0 + s.m) & 1;
+  s.cbase = alm_index(a.lmax, 0, s.m);
+  s.nchunk = (a.lmax - s.l0 + LC) / LC;
+  rec.sp.prev = rec.sp.cur = 0; rec.sp.e = 0;
+  rec.sm.prev = rec.sm.cur = 0; rec.sm.e = 0;
+  rec.x = 0;
+  rec.alive = false;
+  if (s.l0 > a.lmax) return false;
+  const int r = warp * 32 + lane;
+  double sth = 1, chh = 1, shh = 1;
+  if (r < s.nrows) {
+    const i64 rp = a.rp_lo + s.row0 + r;
+    rec.x = a.cth[rp];
     sth = a.sth[rp];
     chh = a.ch[rp];
     shh = a.sh[rp];
+    rec.alive = !ring_is_dead(a.lmax, s.m, SPIN, rec.x, sth);
   }
-  // spin 0: acc[q][c] with q = parity slot (even/odd step inside a chunk)
-  // spin 2: acc[0] = sum lam+ 2a, acc[1] = sum lam- -2a (north); acc[2], acc[3] the southern sums
-  constexpr int NACC = SPIN == 0 ? 2 : 4;
-  constexpr int NCOL = SPIN == 0 ? NB : (NB + 1) / 2;
-  double acc[NACC][NCOL][2];
-#pragma unroll
-  for (int q = 0; q < NACC; ++q)
-#pragma unroll
-    for (int c = 0; c < NCOL; ++c) acc[q][c][0] = acc[q][c][1] = 0.0;
-  const int pb = (l0 + m) & 1;
+  if (__syncthreads_or(rec.alive ? 1 : 0) == 0) return false;  // no ring of this CTA contributes
+  if (rec.alive) lam_start<SPIN>(s.m, a.cmtab, sth, chh, shh, rec.sp, rec.sm);
+  return true;
+}
 
-  if (l0 <= lmax) {
-    const bool alive = valid && !ring_is_dead(lmax, m, SPIN, x, sth);
-    LamState sp, sm;
-    sp.prev = sp.cur = 0; sp.e = 0;
-    sm.prev = sm.cur = 0; sm.e = 0;
-    if (alive) lam_start<SPIN>(m, a.cmtab, sth, chh, shh, sp, sm);
-    const i64 cbase = alm_index(lmax, 0, m);
-    for (int lc = l0; lc <= lmax; lc += LCH) {
-      __syncthreads();
-      // ---- stage a_lm and coefficients of l = lc .. lc + LCH - 1 ----
-      if (SPIN == 0) {
-        for (int idx = threadIdx.x; idx < LCH * NB; idx += 128) {
-          const int li = idx / NB, c = idx - li * NB;
-          const int l = lc + li;
-          double2 v = make_double2(0., 0.);
-          if (l <= lmax && c < a.ncomp) v = reinterpret_cast<const double2 *>(a.alm.p[c])[cbase + l];
-          s_alm[idx] = v;
-        }
-      } else {
-        for (int idx = threadIdx.x; idx < LCH * (NB / 2); idx += 128) {
-          const int li = idx / (NB / 2), f = idx - li * (NB / 2);
-          const int l = lc + li;
-          double2 E = make_double2(0., 0.), B = make_double2(0., 0.);
-          if (l <= lmax && 2 * f < a.ncomp) {
-            E = reinterpret_cast<const double2 *>(a.alm.p[2 * f])[cbase + l];
-            B = reinterpret_cast<const double2 *>(a.alm.p[2 * f + 1])[cbase + l];
-          }
-          // 2a = -(E + iB), -2a = -(E - iB)
-          s_alm[li * NB + 2 * f] = make_double2(-(E.x - B.y), -(E.y + B.x));
-          s_alm[li * NB + 2 * f + 1] = make_double2(-(E.x + B.y), -(E.y - B.x));
-        }
-      }
-      for (int i = threadIdx.x; i < LCH; i += 128) {
-        const int l = lc + i;
-        if (SPIN == 0) {
-          double2 cf = make_double2(0., 0.);
-          if (l < lmax) cf = __ldg(reinterpret_cast<const double2 *>(a.coef) + cbase + l);
-          reinterpret_cast<double2 *>(s_coef)[i] = cf;
-        } else {
-          double4 cf = make_double4(0., 0., 0., 0.);
-          if (l < lmax) cf = ldg_d4(reinterpret_cast<const double4 *>(a.coef) + cbase + l);
-          reinterpret_cast<double4 *>(s_coef)[i] = cf;
-        }
-      }
-      __syncthreads();
-      if (!__any_sync(0xffffffffu, alive)) continue;
-      const bool scaled = __any_sync(0xffffffffu, sp.e < 0 || (SPIN != 0 && sm.e < 0));
-      const bool any_live = __any_sync(0xffffffffu, alive && (sp.e == 0 || (SPIN != 0 && sm.e == 0)));
-      if (!any_live) {
-        // nothing representable yet in this warp: advance the recursions only
-        for (int li = 0; li < LCH; ++li) {
+// ---------------------------------------------------------------------------------
+// analysis
+// ---------------------------------------------------------------------------------
+template <int SPIN, int NBLK>
+struct ACfg {
+  static constexpr int NJ = SPIN == 0 ? 1 : 2;
+  static constexpr int C = 8 * NBLK;
+  static constexpr int TILE = Rec<SPIN>::TILE;
+  static constexpr int WARP = 2 * TILE + 2 * SL * 2;       // two tiles + two coefficient buffers
+  static constexpr int FLUSH = NW * C * FLS;               // one buffer: [warp][col][FLS]
+  static constexpr int FLAG_OFF = NW * WARP + 2 * FLUSH;
+  static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(FLAG_OFF + 2 * NW);
+};
+
+template <int SPIN, int NBLK>
+__global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
+  using K = ACfg<SPIN, NBLK>;
+  constexpr int NJ = K::NJ;
+  extern __shared__ __align__(16) double smem_d[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Setup st;
+  Rec<SPIN> rec;
+  if (!setup_cta<SPIN>(a, st, rec, warp, lane)) return;
+  const int lmax = a.lmax, pb = st.pb;
+  const i64 cbase = st.cbase;
+  double *tiles = smem_d + warp * K::WARP;
+  double *coefs = tiles + 2 * K::TILE;
+  double *flush = smem_d + NW * K::WARP;
+  int *flags = reinterpret_cast<int *>(smem_d + K::FLAG_OFF);
+  const bool warp_alive = __any_sync(0xffffffffu, rec.alive);
+  const int fa = lane & 3;   // k inside a k4 block (A column / B row)
+  const int fb = lane >> 2;  // A row (l) / B column
+
+  // ---- B fragments of this warp's 32 rings, both parities, resident in registers ----
+  double bf[8][NJ][2][NBLK];
+  {
+    const double *src = a.phase + ((i64)st.mi * a.nrp_local + st.row0) * a.ncomp * 4;
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+      const int r = warp * 32 + 4 * k4 + fa;
+      const double *prow = src + (i64)r * a.ncomp * 4;
+#pragma unroll
+      for (int nb = 0; nb < NBLK; ++nb) {
+        const int col = nb * 8 + fb;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
           if (SPIN == 0) {
-            const double2 cf = reinterpret_cast<const double2 *>(s_coef)[li];
-            lam_advance(sp, cf.x * x, cf.y);
+            // column 2c + ri of parity p  <-  (re+, im+, re-, im-)[2p + ri] of map c
+            const int c = col >> 1, ri = col & 1;
+            bf[k4][0][p][nb] = (warp_alive && r < st.nrows && c < a.ncomp) ? prow[c * 4 + 2 * p + ri] : 0.0;
           } else {
-            const double4 cf = reinterpret_cast<const double4 *>(s_coef)[li];
-            lam_advance(sp, fma(cf.x, x, cf.y), cf.z);
-            lam_advance(sm, fma(cf.x, x, -cf.y), cf.z);
-          }
-        }
-        continue;
-      }
-#pragma unroll 2
-      for (int li = 0; li < LCH; li += 2) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const double2 *al = s_alm + (li + q) * NB;
-          if (SPIN == 0) {
-            const double2 cf = reinterpret_cast<const double2 *>(s_coef)[li + q];
-            const double lam = (!scaled || sp.e == 0) ? sp.cur : 0.0;
-#pragma unroll
-            for (int c = 0; c < NB; ++c) {
-              const double2 v = al[c];
-              acc[q][c][0] = fma(lam, v.x, acc[q][c][0]);
-              acc[q][c][1] = fma(lam, v.y, acc[q][c][1]);
+            // column 4f + h, h = (E_re, E_im, B_re, B_im); raw per field: Q (re+ im+ re- im-), U (...)
+            //   E_re = -F+ Q^s_re + F- U^-s_im     E_im = -F+ Q^s_im - F- U^-s_re
+            //   B_re = -F+ U^s_re - F- Q^-s_im     B_im = -F+ U^s_im + F- Q^-s_re
+            // with F+- = (lam+ +- lam-)/2 and s = + for parity 0, - for parity 1, so the
+            // operand of lam+ is (X + Y)/2 and that of lam- is (X - Y)/2.
+            const int f = col >> 2, h = col & 3;
+            // offsets inside the field's 8 doubles: oP = 4 (h >> 1) + (h & 1) + 2 p ; oM mirrors it
+            const int oP = 4 * (h >> 1) + (h & 1) + 2 * p;
+            const int oM = 4 * (1 - (h >> 1)) + (1 - (h & 1)) + 2 * (1 - p);
+            const double sM = (h == 0 || h == 3) ? 1.0 : -1.0;
+            double X = 0.0, Y = 0.0;
+            if (warp_alive && r < st.nrows && 2 * f < a.ncomp) {
+              X = -prow[f * 8 + oP];
+              Y = sM * prow[f * 8 + oM];
             }
-            if (scaled) {
-              lam_advance(sp, cf.x * x, cf.y);
-            } else {
-              const double nw = fma(cf.x * x, sp.cur, -(cf.y * sp.prev));
-              sp.prev = sp.cur;
-              sp.cur = nw;
-            }
-          } else {
-            const double4 cf = reinterpret_cast<const double4 *>(s_coef)[li + q];
-            const double lp = (!scaled || sp.e == 0) ? sp.cur : 0.0;
-            const double lm = (!scaled || sm.e == 0) ? sm.cur : 0.0;
-            // (-1)^(l+m): slot q = 0 has parity pb
-            const double sg = ((q + pb) & 1) ? -1.0 : 1.0;
-            const double slp = sg * lp, slm = sg * lm;
-#pragma unroll
-            for (int f = 0; f < NB / 2; ++f) {
-              const double2 a2 = al[2 * f], m2 = al[2 * f + 1];
-              acc[0][f][0] = fma(lp, a2.x, acc[0][f][0]);
-              acc[0][f][1] = fma(lp, a2.y, acc[0][f][1]);
-              acc[1][f][0] = fma(lm, m2.x, acc[1][f][0]);
-              acc[1][f][1] = fma(lm, m2.y, acc[1][f][1]);
-              // lambda^{+2}(pi - theta) = sg lambda^{-2}(theta) and vice versa
-              acc[2][f][0] = fma(slm, a2.x, acc[2][f][0]);
-              acc[2][f][1] = fma(slm, a2.y, acc[2][f][1]);
-              acc[3][f][0] = fma(slp, m2.x, acc[3][f][0]);
-              acc[3][f][1] = fma(slp, m2.y, acc[3][f][1]);
-            }
-            if (scaled) {
-              lam_advance(sp, fma(cf.x, x, cf.y), cf.z);
-              lam_advance(sm, fma(cf.x, x, -cf.y), cf.z);
-            } else {
-              const double np = fma(fma(cf.x, x, cf.y), sp.cur, -(cf.z * sp.prev));
-              const double nm = fma(fma(cf.x, x, -cf.y), sm.cur, -(cf.z * sm.prev));
-              sp.prev = sp.cur; sp.cur = np;
-              sm.prev = sm.cur; sm.cur = nm;
-            }
+            bf[k4][0][p][nb] = 0.5 * (X + Y);
+            bf[k4][1][p][nb] = 0.5 * (X - Y);
           }
         }
       }
     }
   }
-  if (!valid) return;
-  double *dst = phase_out + ((i64)m * a.nrp_local + rp) * a.ncomp * 4;
-  if (SPIN == 0) {
-    // slot q = 0 holds the terms with (l+m) parity pb
+
+  const int ring = lane;  // ring of this lane inside the warp's tile
+  const int nsub = 2 * st.nchunk;
+  double n_rec = 0, n_acc = 0;
+  // ---- prologue: sub-chunk 0 ----
+  bool live_cur = false, live_nxt = false;
+  stage_coef<SPIN>(coefs, a, cbase, st.l0, lane);
+  __syncwarp();
+  if (warp_alive) {
+    live_cur = rec.sub_live();
+    rec.begin_sub();
 #pragma unroll
-    for (int c = 0; c < NB; ++c) {
-      if (c < a.ncomp) {
-        const double er = pb ? acc[1][c][0] : acc[0][c][0], ei = pb ? acc[1][c][1] : acc[0][c][1];
-        const double orr = pb ? acc[0][c][0] : acc[1][c][0], oi = pb ? acc[0][c][1] : acc[1][c][1];
-        *reinterpret_cast<double4 *>(dst + c * 4) = make_double4(er + orr, ei + oi, er - orr, ei - oi);
+    for (int s = 0; s < SL; s += 4) rec.step4(tiles, coefs, ring, pb, s);
+    rec.end_sub();
+    n_rec += 1;
+  }
+  // flush assignment of this thread: l index within the chunk tid & 31, columns (tid >> 5) + 8 i
+  const int f_lidx = threadIdx.x & 31;
+  const int f_p = f_lidx >> 4, f_idx = f_lidx & 15;
+
+  for (int chk = 0; chk < st.nchunk; ++chk) {
+    const int lstart = st.l0 + chk * LC;
+    // scale of this thread's flush outputs, fetched a chunk's worth of work ahead
+    const int f_l = lstart + 2 * f_idx + (f_p ^ pb);
+    double f_sc = 0.0;
+    if (f_l <= lmax) {
+      f_sc = __ldg(a.scale + cbase + f_l);
+      if (a.fl) f_sc *= __ldg(a.fl + f_l);
+    }
+    double acc[2][2][NBLK][2];  // [parity][sub-chunk][n-block][2]
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int sb = 0; sb < 2; ++sb)
+#pragma unroll
+        for (int nb = 0; nb < NBLK; ++nb) acc[p][sb][nb][0] = acc[p][sb][nb][1] = 0.0;
+    bool chunk_live = false;
+#pragma unroll
+    for (int sb = 0; sb < 2; ++sb) {
+      const int sidx = 2 * chk + sb;
+      const double *tcur = tiles + (sidx & 1) * K::TILE;
+      double *tnxt = tiles + ((sidx + 1) & 1) * K::TILE;
+      const double *ccur = coefs + ((sidx + 1) & 1) * (SL * 2);
+      // the recursion always runs one sub-chunk ahead (the one past the end is harmless: its
+      // coefficients are zero and nothing reads it) so that the hot path below is branch free
+      const bool prod = warp_alive;
+      __syncwarp();
+      if (prod) stage_coef<SPIN>(coefs + ((sidx + 1) & 1) * (SL * 2), a, cbase, st.l0 + (sidx + 1) * SL, lane);
+      __syncwarp();  // tile `sidx` and the coefficients of sub-chunk sidx + 1 are in place
+      if (prod) {
+        live_nxt = rec.sub_live();
+        rec.begin_sub();
+        if (sidx + 1 < nsub) n_rec += 1;
+      }
+      if (live_cur) {
+        chunk_live = true;
+        n_acc += 1;
+        // DMMAs of sub-chunk sidx interleaved with the recursion of sub-chunk sidx + 1
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const int r = 4 * k4 + fa;
+          const int off = lam_off(r, fb);
+          double af[NJ][2];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int p = 0; p < 2; ++p) af[j][p] = tcur[(2 * j + p) * 256 + off];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+              for (int nb = 0; nb < NBLK; ++nb)
+                dmma(acc[p][sb][nb][0], acc[p][sb][nb][1], af[j][p], bf[k4][j][p][nb]);
+          if (k4 & 1) rec.step4(tnxt, ccur, ring, pb, (k4 >> 1) * 4);
+        }
+      } else if (prod) {
+#pragma unroll
+        for (int s = 0; s < SL; s += 4) rec.step4(tnxt, ccur, ring, pb, s);
+      }
+      if (prod) rec.end_sub();
+      live_cur = prod ? live_nxt : false;
+    }
+    // ---- reduce the eight warps' partial tiles of this chunk and add to alm ----
+    double *fbuf = flush + (chk & 1) * K::FLUSH;
+    if (lane == 0) flags[(chk & 1) * NW + warp] = chunk_live ? 1 : 0;
+    if (chunk_live) {
+      double *o = fbuf + warp * (K::C * FLS);
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int sb = 0; sb < 2; ++sb)
+#pragma unroll
+          for (int nb = 0; nb < NBLK; ++nb) {
+            double *d = o + (nb * 8 + 2 * fa) * FLS + p * 16 + sb * 8 + fb;
+            d[0] = acc[p][sb][nb][0];
+            d[FLS] = acc[p][sb][nb][1];
+          }
+    }
+    __syncthreads();
+    int lv[NW], any = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      lv[w] = flags[(chk & 1) * NW + w];
+      any |= lv[w];
+    }
+    if (any && f_l <= lmax) {
+#pragma unroll
+      for (int i = 0; i < NBLK; ++i) {
+        const int col = (threadIdx.x >> 5) + 8 * i;
+        int row, ri;
+        if (SPIN == 0) {
+          row = col >> 1;
+          ri = col & 1;
+        } else {
+          row = 2 * (col >> 2) + ((col >> 1) & 1);
+          ri = col & 1;
+        }
+        if (row < a.ncomp) {
+          double sum = 0.0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w)
+            if (lv[w]) sum += fbuf[w * (K::C * FLS) + col * FLS + f_lidx];
+          atomicAdd(a.alm.p[row] + 2 * (cbase + f_l) + ri, sum * f_sc);
+        }
       }
     }
-  } else {
+  }
+  if (lane == 0 && a.work && n_rec > 0) {
+    atomicAdd(a.work, n_rec * 32.0 * SL);
+    atomicAdd(a.work + 1, n_acc * 32.0 * SL);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// synthesis
+// ---------------------------------------------------------------------------------
+template <int SPIN, int NBLK>
+struct SCfg {
+  static constexpr int NJ = SPIN == 0 ? 1 : 2;
+  static constexpr int C = 8 * NBLK;
+  static constexpr int NU = SPIN == 0 ? 4 * NBLK : 4;      // maps resp. fields per batch
+  static constexpr int NLOAD = SPIN == 0 ? NU : 2 * NU;    // alm rows fetched per lane and chunk
+  static constexpr int BSTR = C + 4;                       // 12 or 4 (mod 16): conflict free B fragments
+  static constexpr int TILE = Rec<SPIN>::TILE;
+  static constexpr int WARP = 2 * TILE + 2 * SL * 2 + LC * BSTR;
+  static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(NW * WARP);
+  static_assert(SPIN == 0 || NBLK == 2, "spin 2 synthesis uses the (a2 | m2) two-block column layout");
+};
+
+template <int SPIN, int NBLK>
+__global__ void __launch_bounds__(NT, 1) legendre_synthesis_kernel(LegArgs a) {
+  using K = SCfg<SPIN, NBLK>;
+  constexpr int NJ = K::NJ;
+  extern __shared__ __align__(16) double smem_d[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Setup st;
+  Rec<SPIN> rec;
+  const bool active = setup_cta<SPIN>(a, st, rec, warp, lane);
+  double *dst = a.phase_out + ((i64)st.mi * a.nrp_local + st.row0) * a.ncomp * 4;
+  if (!active) {  // every output row must be defined
+    for (int i = threadIdx.x; i < st.nrows * a.ncomp * 4; i += NT) dst[i] = 0.0;
+    return;
+  }
+  const int lmax = a.lmax, pb = st.pb;
+  const i64 cbase = st.cbase;
+  double *tiles = smem_d + warp * K::WARP;
+  double *coefs = tiles + 2 * K::TILE;
+  double *btile = coefs + 2 * SL * 2;  // [parity][16][BSTR]: s_l a_lm of the current chunk
+  const bool warp_alive = __any_sync(0xffffffffu, rec.alive);
+  const int fa = lane & 3;   // k inside a k4 block (A column = l / B row = l)
+  const int fb = lane >> 2;  // A row (ring) / B column
+
+  // spin 0: acc[parity][mb][nb]; spin 2: acc[j][mb][block], block 0 = (+2a) columns, block 1 = (-2a) columns
+  double acc[2][4][NBLK][2];
 #pragma unroll
-    for (int f = 0; f < NB / 2; ++f) {
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < NBLK; ++nb) acc[i][mb][nb][0] = acc[i][mb][nb][1] = 0.0;
+
+  // a_lm of one chunk: lane = l row.  Fetch into registers, convert and park in btile later.
+  double2 av[K::NLOAD];
+  auto fetch_alm = [&](int lstart) {
+    const int l = lstart + lane;
+#pragma unroll
+    for (int i = 0; i < K::NLOAD; ++i) {
+      av[i] = make_double2(0., 0.);
+      if (warp_alive && l <= lmax && i < a.ncomp)
+        av[i] = reinterpret_cast<const double2 *>(a.alm.p[i])[cbase + l];
+    }
+  };
+  auto park_alm = [&](int lstart) {
+    const int l = lstart + lane;
+    const double sc = (warp_alive && l <= lmax) ? __ldg(a.scale + cbase + l) : 0.0;
+    // step `lane` of the chunk has parity pb ^ (lane & 1), l index lane >> 1 within the parity
+    double *row = btile + ((pb ^ (lane & 1)) * 16 + (lane >> 1)) * K::BSTR;
+    if (SPIN == 0) {
+#pragma unroll
+      for (int i = 0; i < K::NLOAD; ++i)
+        *reinterpret_cast<double2 *>(row + 2 * i) = make_double2(av[i].x * sc, av[i].y * sc);
+    } else {
+#pragma unroll
+      for (int f = 0; f < K::NU; ++f) {
+        const double2 E = av[2 * f], B = av[2 * f + 1];
+        // +2a = -(E + iB) -> block 0, -2a = -(E - iB) -> block 1
+        *reinterpret_cast<double2 *>(row + 2 * f) = make_double2(-(E.x - B.y) * sc, -(E.y + B.x) * sc);
+        *reinterpret_cast<double2 *>(row + 8 + 2 * f) = make_double2(-(E.x + B.y) * sc, -(E.y - B.x) * sc);
+      }
+    }
+  };
+
+  const int ring = lane;
+  bool live_cur = false, live_nxt = false;
+  // ---- prologue: sub-chunk 0 and the a_lm of chunk 0 ----
+  fetch_alm(st.l0);
+  stage_coef<SPIN>(coefs, a, cbase, st.l0, lane);
+  __syncwarp();
+  if (warp_alive) {
+    live_cur = rec.sub_live();
+    rec.begin_sub();
+#pragma unroll
+    for (int s = 0; s < SL; s += 4) rec.step4(tiles, coefs, ring, pb, s);
+    rec.end_sub();
+  }
+  park_alm(st.l0);
+
+  for (int chk = 0; chk < st.nchunk; ++chk) {
+    if (chk + 1 < st.nchunk) fetch_alm(st.l0 + (chk + 1) * LC);
+#pragma unroll
+    for (int sb = 0; sb < 2; ++sb) {
+      const int sidx = 2 * chk + sb;
+      const double *tcur = tiles + (sidx & 1) * K::TILE;
+      double *tnxt = tiles + ((sidx + 1) & 1) * K::TILE;
+      const double *ccur = coefs + ((sidx + 1) & 1) * (SL * 2);
+      const bool prod = warp_alive;  // one sub-chunk ahead, also past the end (see the analysis kernel)
+      __syncwarp();
+      if (prod) stage_coef<SPIN>(coefs + ((sidx + 1) & 1) * (SL * 2), a, cbase, st.l0 + (sidx + 1) * SL, lane);
+      __syncwarp();  // tile `sidx`, btile and the coefficients of sub-chunk sidx + 1 are in place
+      if (prod) {
+        live_nxt = rec.sub_live();
+        rec.begin_sub();
+      }
+      if (live_cur) {
+        // k4 steps: (parity p, half h) -> rows p*16 + sb*8 + 4h + fa of btile, l index 4h + fa of the tile
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+          const int p = ph >> 1, h = ph & 1;
+          const double *brow = btile + (p * 16 + sb * 8 + 4 * h + fa) * K::BSTR + fb;
+          double bfr[NBLK];
+#pragma unroll
+          for (int nb = 0; nb < NBLK; ++nb) bfr[nb] = brow[nb * 8];
+#pragma unroll
+          for (int mb = 0; mb < 4; ++mb) {
+            const int off = lam_off(mb * 8 + fb, 4 * h + fa);
+            if (SPIN == 0) {
+              const double av0 = tcur[p * 256 + off];
+#pragma unroll
+              for (int nb = 0; nb < NBLK; ++nb) dmma(acc[p][mb][nb][0], acc[p][mb][nb][1], av0, bfr[nb]);
+            } else {
+              // acc[0][.][0] = P_N = sum lam+ (+2a)        acc[0][.][1] = M_S = sum sg lam+ (-2a)
+              // acc[1][.][0] = P_S = sum sg lam- (+2a)     acc[1][.][1] = M_N = sum lam- (-2a)
+              // sg = (-1)^(l+m): the sign goes onto the A fragment (integer pipe)
+              const double lp = tcur[p * 256 + off], lm = tcur[(2 + p) * 256 + off];
+              const double lps = p ? neg_d(lp) : lp, lms = p ? neg_d(lm) : lm;
+              dmma(acc[0][mb][0][0], acc[0][mb][0][1], lp, bfr[0]);
+              dmma(acc[0][mb][1][0], acc[0][mb][1][1], lps, bfr[1]);
+              dmma(acc[1][mb][0][0], acc[1][mb][0][1], lms, bfr[0]);
+              dmma(acc[1][mb][1][0], acc[1][mb][1][1], lm, bfr[1]);
+            }
+          }
+          rec.step4(tnxt, ccur, ring, pb, ph * 4);
+        }
+      } else if (prod) {
+#pragma unroll
+        for (int s = 0; s < SL; s += 4) rec.step4(tnxt, ccur, ring, pb, s);
+      }
+      if (prod) rec.end_sub();
+      live_cur = prod ? live_nxt : false;
+    }
+    if (chk + 1 < st.nchunk) {
+      __syncwarp();  // every lane is done reading btile
+      park_alm(st.l0 + (chk + 1) * LC);
+    }
+  }
+
+  // ---- results straight from the accumulator fragments: lane holds ring mb*8+fb, unit fa (+4 nb) ----
+  if (!warp_alive) {
+    for (int i = lane; i < 32 * a.ncomp * 4; i += 32) {
+      const int r = warp * 32 + i / (a.ncomp * 4);
+      if (r < st.nrows) dst[(i64)warp * 32 * a.ncomp * 4 + i] = 0.0;
+    }
+    return;
+  }
+#pragma unroll
+  for (int mb = 0; mb < 4; ++mb) {
+    const int r = warp * 32 + mb * 8 + fb;
+    if (r >= st.nrows) continue;
+    if (SPIN == 0) {
+      // parity 0 = (l + m) even: north = T0 + T1, south = T0 - T1
+#pragma unroll
+      for (int nb = 0; nb < NBLK; ++nb) {
+        const int c = nb * 4 + fa;
+        if (c < a.ncomp) {
+          const double t0r = acc[0][mb][nb][0], t0i = acc[0][mb][nb][1];
+          const double t1r = acc[1][mb][nb][0], t1i = acc[1][mb][nb][1];
+          *reinterpret_cast<double4 *>(dst + ((i64)r * a.ncomp + c) * 4) =
+              make_double4(t0r + t1r, t0i + t1i, t0r - t1r, t0i - t1i);
+        }
+      }
+    } else {
+      const int f = fa;
       if (2 * f < a.ncomp) {
-        const double PrN = acc[0][f][0], PiN = acc[0][f][1], MrN = acc[1][f][0], MiN = acc[1][f][1];
-        const double PrS = acc[2][f][0], PiS = acc[2][f][1], MrS = acc[3][f][0], MiS = acc[3][f][1];
+        const double PrN = acc[0][mb][0][0], PiN = acc[0][mb][0][1];
+        const double MrS = acc[0][mb][1][0], MiS = acc[0][mb][1][1];
+        const double PrS = acc[1][mb][0][0], PiS = acc[1][mb][0][1];
+        const double MrN = acc[1][mb][1][0], MiN = acc[1][mb][1][1];
+        double *d = dst + ((i64)r * a.ncomp + 2 * f) * 4;
         // Q = (P + M)/2 ; U = (P - M)/(2i)
-        *reinterpret_cast<double4 *>(dst + (2 * f) * 4) =
+        *reinterpret_cast<double4 *>(d) =
             make_double4(0.5 * (PrN + MrN), 0.5 * (PiN + MiN), 0.5 * (PrS + MrS), 0.5 * (PiS + MiS));
-        *reinterpret_cast<double4 *>(dst + (2 * f + 1) * 4) =
+        *reinterpret_cast<double4 *>(d + 4) =
             make_double4(0.5 * (PiN - MiN), -0.5 * (PrN - MrN), 0.5 * (PiS - MiS), -0.5 * (PrS - MrS));
       }
     }
   }
 }
 
-// recursion coefficient tables: step l -> l+1 for l >= l0
-//   spin 0: (alpha_l, gamma_l),  L_{l+1} = alpha x L_l - gamma L_{l-1}
-//   spin 2: (alpha_l, alpha_l beta_l, gamma_l, 0),  L^{+-}_{l+1} = (alpha x +- alpha beta) L_l - gamma L_{l-1}
-__global__ void coef_kernel(int lmax, int spin, double *tab) {
-  const int m = blockIdx.x;
+// recursion tables, one thread per m (sequential in l because of the running scale s_l):
+//   lambda_{l+1} = (alpha_l x +- alpha_l beta_l) lambda_l - gamma_l lambda_{l-1},  l >= l0 = max(m, spin)
+//   lambda_l = s_l q_l with s_{l0} = s_{l0+1} = 1, s_{l+1} = gamma_l s_{l-1}, which turns it into
+//   q_{l+1} = (A_l x +- B_l) q_l - q_{l-1},  A_l = alpha_l s_l / s_{l+1},  B_l = alpha_l beta_l s_l / s_{l+1}
+// tab: spin 0 double A_l; spin 2 double2 (A_l, B_l); scale: s_l.  Index cbase(m) + l.
+__global__ void coef_kernel(int lmax, int spin, double *tab, double *scale) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m > lmax) return;
   const int s = spin;
   const int l0 = m > s ? m : s;
   const i64 base = (i64)m * (2 * lmax + 1 - m) / 2;
-  for (int l = m + threadIdx.x; l <= lmax; l += blockDim.x) {
-    double al = 0, ab = 0, ga = 0;
-    if (l >= l0 && l < lmax) {
-      const double dl = l, l1 = dl + 1.0, dm = m, ds = s;
-      const double den = sqrt((l1 * l1 - dm * dm) * (l1 * l1 - ds * ds));
-      al = sqrt((2 * dl + 3) / (2 * dl + 1)) * l1 * (2 * dl + 1) / den;
-      const double be = (l > 0) ? (ds * dm) / (dl * l1) : 0.0;
-      ab = al * be;
-      ga = (l > l0) ? sqrt((2 * dl + 3) / (2 * dl - 1)) * l1 / dl *
-                          sqrt((dl * dl - dm * dm) * (dl * dl - ds * ds)) / den
-                    : 0.0;
+  double s_prev = 1.0, s_cur = 1.0;  // s_{l-1}, s_l
+  for (int l = m; l <= lmax; ++l) {
+    double A = 0, B = 0, sc = 0;
+    if (l >= l0) {
+      sc = s_cur;
+      if (l < lmax) {
+        const double dl = l, l1 = dl + 1.0, dm = m, ds = s;
+        const double den = sqrt((l1 * l1 - dm * dm) * (l1 * l1 - ds * ds));
+        const double al = sqrt((2 * dl + 3) / (2 * dl + 1)) * l1 * (2 * dl + 1) / den;
+        const double be = (l > 0) ? (ds * dm) / (dl * l1) : 0.0;
+        const double ga = (l > l0) ? sqrt((2 * dl + 3) / (2 * dl - 1)) * l1 / dl *
+                                         sqrt((dl * dl - dm * dm) * (dl * dl - ds * ds)) / den
+                                   : 0.0;
+        const double s_next = (l > l0) ? ga * s_prev : 1.0;
+        A = al * s_cur / s_next;
+        B = al * be * s_cur / s_next;
+        s_prev = s_cur;
+        s_cur = s_next;
+      }
     }
     if (s == 0) {
-      reinterpret_cast<double2 *>(tab)[base + l] = make_double2(al, ga);
+      tab[base + l] = A;
     } else {
-      reinterpret_cast<double4 *>(tab)[base + l] = make_double4(al, ab, ga, 0.0);
+      reinterpret_cast<double2 *>(tab)[base + l] = make_double2(A, B);
     }
+    scale[base + l] = sc;
   }
 }
 
-template <int SPIN, int NB>
-int launch_synthesis(hcu_ctx *ctx, const LegArgs &a, double *phase_out) {
-  const int ngroups = (int)((a.nrp_local + 127) / 128);
-  const i64 nblocks = (i64)ngroups * (a.lmax + 1);
-  legendre_synthesis_kernel<SPIN, NB><<<(unsigned)nblocks, 128, 0, ctx->stream>>>(a, phase_out);
+template <int SPIN, int NBLK>
+int launch_analysis(hcu_ctx *ctx, const LegArgs &a) {
+  using K = ACfg<SPIN, NBLK>;
+  const i64 nblocks = (i64)((a.nrp_local + R - 1) / R) * a.nm;
+  if (nblocks <= 0) return HCU_OK;
+  HCU_CUDA(cudaFuncSetAttribute(legendre_analysis_kernel<SPIN, NBLK>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
+  legendre_analysis_kernel<SPIN, NBLK><<<(unsigned)nblocks, NT, K::SMEM_BYTES, ctx->stream>>>(a);
   HCU_LAUNCH_CHECK(ctx);
   return HCU_OK;
 }
 
+template <int SPIN, int NBLK>
+int launch_synthesis(hcu_ctx *ctx, const LegArgs &a) {
+  using K = SCfg<SPIN, NBLK>;
+  const i64 nblocks = (i64)((a.nrp_local + R - 1) / R) * a.nm;
+  if (nblocks <= 0) return HCU_OK;
+  HCU_CUDA(cudaFuncSetAttribute(legendre_synthesis_kernel<SPIN, NBLK>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
+  legendre_synthesis_kernel<SPIN, NBLK><<<(unsigned)nblocks, NT, K::SMEM_BYTES, ctx->stream>>>(a);
+  HCU_LAUNCH_CHECK(ctx);
+  return HCU_OK;
+}
+
+void fill_args(LegArgs &a, hcu_geom *g, hcu_coef *c, int lmax, int ncomp,
+               const int32_t *mlist_dev, int nm, i64 rp_lo, i64 rp_hi) {
+  a.lmax = lmax;
+  a.nm = nm;
+  a.ncomp = ncomp;
+  a.mlist = mlist_dev;
+  a.phase = nullptr;
+  a.nrp_local = rp_hi - rp_lo;
+  a.rp_lo = rp_lo;
+  a.cth = g->cth;
+  a.sth = g->sth;
+  a.ch = g->ch;
+  a.sh = g->sh;
+  a.coef = c->tab;
+  a.scale = c->scale;
+  a.cmtab = c->cm;
+  a.fl = nullptr;
+  a.phase_out = nullptr;
+  a.work = nullptr;
+}
+
 }  // namespace
+
+int hcu_legendre_batch(int spin) { return spin == 0 ? 12 : 8; }
 
 int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c) {
   const i64 nalm = (i64)(c->lmax + 1) * (c->lmax + 2) / 2;
-  const size_t per = (c->spin == 0) ? 2 : 4;
+  const size_t per = (c->spin == 0) ? 1 : 2;
   HCU_CUDA(cudaMalloc(&c->tab, sizeof(double) * per * nalm));
-  coef_kernel<<<c->lmax + 1, 128, 0, ctx->stream>>>(c->lmax, c->spin, c->tab);
+  HCU_CUDA(cudaMalloc(&c->scale, sizeof(double) * nalm));
+  coef_kernel<<<(c->lmax + 64) / 64, 64, 0, ctx->stream>>>(c->lmax, c->spin, c->tab, c->scale);
   HCU_LAUNCH_CHECK(ctx);
   // start-value normalisation in long double on the host:
   //   cm[2m] = c_m with lambda_mm = (-1)^m c_m sin^m(theta);  cm[2m+1] = c_m sqrt(m(m-1)/((m+1)(m+2)))
@@ -259,40 +695,46 @@ int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c) {
   return HCU_OK;
 }
 
-int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
-                           int spin, int ncomp, const hcu_ptrs &alm, double *phase) {
-  HCU_ARG(ncomp >= 1 && ncomp <= HCU_MAX_BATCH, "synthesis batch size");
+// alm[c][l, m] += sum over ring pairs [rp_lo, rp_hi) of lambda_lm(theta) x phase, for m in mlist
+int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
+                          int spin, int ncomp, const double *phase,
+                          const int32_t *mlist_dev, int nm, i64 rp_lo, i64 rp_hi,
+                          const double *fl_dev, const hcu_ptrs &alm) {
+  HCU_ARG(ncomp >= 1 && ncomp <= hcu_legendre_batch(spin), "legendre batch size");
   LegArgs a;
-  a.lmax = lmax;
-  a.nm = lmax + 1;
-  a.ncomp = ncomp;
-  a.mlist = nullptr;
-  a.phase = nullptr;
-  a.nrp_local = g->nrp;
-  a.rp_lo = 0;
-  a.cth = g->cth;
-  a.sth = g->sth;
-  a.ch = g->ch;
-  a.sh = g->sh;
-  a.coef = c->tab;
-  a.cmtab = c->cm;
-  a.fl = nullptr;
+  fill_args(a, g, c, lmax, ncomp, mlist_dev, nm, rp_lo, rp_hi);
+  a.phase = phase;
+  a.fl = fl_dev;
   a.alm = alm;
-  a.work = nullptr;
+  a.work = ctx->work_counters;
+  // 8 output columns per n-block: 4 spin-0 maps, or 2 spin-2 fields (4 Q/U rows)
+  const int nblk = (ncomp + 3) / 4;
   if (spin == 0) {
-    if (ncomp <= 1) return launch_synthesis<0, 1>(ctx, a, phase);
-    if (ncomp <= 2) return launch_synthesis<0, 2>(ctx, a, phase);
-    if (ncomp <= 4) return launch_synthesis<0, 4>(ctx, a, phase);
-    if (ncomp <= 6) return launch_synthesis<0, 6>(ctx, a, phase);
-    if (ncomp <= 8) return launch_synthesis<0, 8>(ctx, a, phase);
-    if (ncomp <= 10) return launch_synthesis<0, 10>(ctx, a, phase);
-    return launch_synthesis<0, 12>(ctx, a, phase);
-  } else {
-    if (ncomp <= 2) return launch_synthesis<2, 2>(ctx, a, phase);
-    if (ncomp <= 4) return launch_synthesis<2, 4>(ctx, a, phase);
-    if (ncomp <= 6) return launch_synthesis<2, 6>(ctx, a, phase);
-    if (ncomp <= 8) return launch_synthesis<2, 8>(ctx, a, phase);
-    if (ncomp <= 10) return launch_synthesis<2, 10>(ctx, a, phase);
-    return launch_synthesis<2, 12>(ctx, a, phase);
+    switch (nblk) {
+      case 1: return launch_analysis<0, 1>(ctx, a);
+      case 2: return launch_analysis<0, 2>(ctx, a);
+      default: return launch_analysis<0, 3>(ctx, a);
+    }
   }
+  return nblk == 1 ? launch_analysis<2, 1>(ctx, a) : launch_analysis<2, 2>(ctx, a);
+}
+
+// phase[(mi * nrp_local + rp - rp_lo) * ncomp + c] = (reN, imN, reS, imS) of sum_l a_lm lambda_lm(theta_rp)
+int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
+                           int spin, int ncomp, const hcu_ptrs &alm,
+                           const int32_t *mlist_dev, int nm, i64 rp_lo, i64 rp_hi,
+                           double *phase) {
+  HCU_ARG(ncomp >= 1 && ncomp <= hcu_legendre_batch(spin), "synthesis batch size");
+  LegArgs a;
+  fill_args(a, g, c, lmax, ncomp, mlist_dev, nm, rp_lo, rp_hi);
+  a.alm = alm;
+  a.phase_out = phase;
+  if (spin == 0) {
+    switch ((ncomp + 3) / 4) {
+      case 1: return launch_synthesis<0, 1>(ctx, a);
+      case 2: return launch_synthesis<0, 2>(ctx, a);
+      default: return launch_synthesis<0, 3>(ctx, a);
+    }
+  }
+  return launch_synthesis<2, 2>(ctx, a);
 }

@@ -53,8 +53,9 @@ __device__ __forceinline__ void set_scaled(LamState &s, double mant, int k) {
   s.e = e;
 }
 
-__device__ __forceinline__ void lam_advance(LamState &s, double ax, double g) {
-  double nw = fma(ax, s.cur, -(g * s.prev));
+// one step of the scaled recursion q_{l+1} = ax q_l - q_{l-1} with extended-exponent rescaling
+__device__ __forceinline__ void lam_advance(LamState &s, double ax) {
+  double nw = fma(ax, s.cur, -s.prev);
   s.prev = s.cur;
   s.cur = nw;
   if (s.e < 0 && fabs(nw) >= TWO_P200) {
@@ -131,9 +132,11 @@ struct LegArgs {
   i64 nrp_local, rp_lo;
   const double *cth, *sth, *ch, *sh;  // indexed by global ring pair
   const double *coef;       // recursion coefficients, see hcu_build_coef
+  const double *scale;      // s_l of the scaled recursion, lambda_l = s_l q_l
   const double *cmtab;
   const double *fl;         // nullptr or [lmax+1]
   hcu_ptrs alm;             // one complex128 row per component
+  double *phase_out;        // synthesis output, same layout as `phase` with (reN, imN, reS, imS)
   double *work;             // [2] counters
 };
 
