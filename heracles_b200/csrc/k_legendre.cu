@@ -126,19 +126,54 @@ struct Rec {
   }
 };
 
+// prefetch loads: `asm volatile` pins them where they are written, a full sub-chunk (or chunk)
+// of tensor work ahead of their first use, instead of letting ptxas sink them next to it
+__device__ __forceinline__ double ldg_pin(const double *p) {
+  double r;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ldg_pin2(const double2 *p) {
+  double2 r;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
 // lanes 0..15 fetch the recursion coefficients of the 16 steps starting at l = lsub
 template <int SPIN>
-__device__ __forceinline__ void stage_coef(double *cf, const LegArgs &a, i64 cbase, int lsub, int lane) {
+__device__ __forceinline__ double2 fetch_coef(const LegArgs &a, i64 cbase, int lsub, int lane) {
+  double2 c2 = make_double2(0., 0.);
   if (lane < SL) {
-    double2 c2 = make_double2(0., 0.);
     const int l = lsub + lane;
-    if (l < a.lmax) {
-      if (SPIN == 0)
-        c2.x = __ldg(a.coef + cbase + l);
-      else
-        c2 = __ldg(reinterpret_cast<const double2 *>(a.coef) + cbase + l);
-    }
-    reinterpret_cast<double2 *>(cf)[lane] = c2;
+    const int lc = min(l, max(a.lmax - 1, 0));  // clamped: the load is unconditional
+    if (SPIN == 0)
+      c2.x = ldg_pin(a.coef + cbase + lc);
+    else
+      c2 = ldg_pin2(reinterpret_cast<const double2 *>(a.coef) + cbase + lc);
+    if (l >= a.lmax) c2 = make_double2(0., 0.);
+  }
+  return c2;
+}
+__device__ __forceinline__ void park_coef(double *cf, double2 c2, int lane) {
+  if (lane < SL) reinterpret_cast<double2 *>(cf)[lane] = c2;
+}
+
+// split-phase CTA barrier (arrive now, wait a chunk later) for the deferred alm flush
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, int parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
   }
 }
 
@@ -189,8 +224,8 @@ struct ACfg {
   static constexpr int TILE = Rec<SPIN>::TILE;
   static constexpr int WARP = 2 * TILE + 2 * SL * 2;       // two tiles + two coefficient buffers
   static constexpr int FLUSH = NW * C * FLS;               // one buffer: [warp][col][FLS]
-  static constexpr int FLAG_OFF = NW * WARP + 2 * FLUSH;
-  static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(FLAG_OFF + 2 * NW);
+  static constexpr int FLAG_OFF = NW * WARP + 2 * FLUSH;   // 2 x NW ints, then two mbarriers
+  static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(FLAG_OFF + NW + 2);
 };
 
 template <int SPIN, int NBLK>
@@ -208,9 +243,15 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
   double *coefs = tiles + 2 * K::TILE;
   double *flush = smem_d + NW * K::WARP;
   int *flags = reinterpret_cast<int *>(smem_d + K::FLAG_OFF);
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_d + K::FLAG_OFF + NW);
   const bool warp_alive = __any_sync(0xffffffffu, rec.alive);
   const int fa = lane & 3;   // k inside a k4 block (A column / B row)
   const int fb = lane >> 2;  // A row (l) / B column
+  if (threadIdx.x == 0) {
+    mbar_init(mbar, NW);
+    mbar_init(mbar + 1, NW);
+  }
+  __syncthreads();
 
   // ---- B fragments of this warp's 32 rings, both parities, resident in registers ----
   double bf[8][NJ][2][NBLK];
@@ -258,7 +299,8 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
   double n_rec = 0, n_acc = 0;
   // ---- prologue: sub-chunk 0 ----
   bool live_cur = false, live_nxt = false;
-  stage_coef<SPIN>(coefs, a, cbase, st.l0, lane);
+  park_coef(coefs, fetch_coef<SPIN>(a, cbase, st.l0, lane), lane);
+  double2 cnext = fetch_coef<SPIN>(a, cbase, st.l0 + SL, lane);  // coefficients of sub-chunk 1
   __syncwarp();
   if (warp_alive) {
     live_cur = rec.sub_live();
@@ -272,15 +314,48 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
   const int f_lidx = threadIdx.x & 31;
   const int f_p = f_lidx >> 4, f_idx = f_lidx & 15;
 
+  // the reduction of chunk c over the eight warps is deferred to the end of chunk c + 1, so that
+  // nobody waits at a barrier: partial tiles and flags are double buffered, mbar[c & 1] counts the warps
+  int f_l_prev = 0;
+  double f_sc_prev = 0.0;
+  auto reduce_chunk = [&](int c, int f_l, double f_sc) {
+    mbar_wait(mbar + (c & 1), (c >> 1) & 1);
+    const double *fbuf = flush + (c & 1) * K::FLUSH;
+    int lv[NW], any = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      lv[w] = flags[(c & 1) * NW + w];
+      any |= lv[w];
+    }
+    if (any && f_l <= lmax) {
+#pragma unroll
+      for (int i = 0; i < NBLK; ++i) {
+        const int col = (threadIdx.x >> 5) + 8 * i;
+        int row, ri;
+        if (SPIN == 0) {
+          row = col >> 1;
+          ri = col & 1;
+        } else {
+          row = 2 * (col >> 2) + ((col >> 1) & 1);
+          ri = col & 1;
+        }
+        if (row < a.ncomp) {
+          double sum = 0.0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w)
+            if (lv[w]) sum += fbuf[w * (K::C * FLS) + col * FLS + f_lidx];
+          atomicAdd(a.alm.p[row] + 2 * (cbase + f_l) + ri, sum * f_sc);
+        }
+      }
+    }
+  };
+
   for (int chk = 0; chk < st.nchunk; ++chk) {
     const int lstart = st.l0 + chk * LC;
     // scale of this thread's flush outputs, fetched a chunk's worth of work ahead
     const int f_l = lstart + 2 * f_idx + (f_p ^ pb);
-    double f_sc = 0.0;
-    if (f_l <= lmax) {
-      f_sc = __ldg(a.scale + cbase + f_l);
-      if (a.fl) f_sc *= __ldg(a.fl + f_l);
-    }
+    double f_sc = ldg_pin(a.scale + cbase + min(f_l, lmax));
+    const double f_fl = a.fl ? ldg_pin(a.fl + min(f_l, lmax)) : 1.0;
     double acc[2][2][NBLK][2];  // [parity][sub-chunk][n-block][2]
 #pragma unroll
     for (int p = 0; p < 2; ++p)
@@ -299,7 +374,10 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
       // coefficients are zero and nothing reads it) so that the hot path below is branch free
       const bool prod = warp_alive;
       __syncwarp();
-      if (prod) stage_coef<SPIN>(coefs + ((sidx + 1) & 1) * (SL * 2), a, cbase, st.l0 + (sidx + 1) * SL, lane);
+      if (prod) {
+        park_coef(coefs + ((sidx + 1) & 1) * (SL * 2), cnext, lane);
+        cnext = fetch_coef<SPIN>(a, cbase, st.l0 + (sidx + 2) * SL, lane);
+      }
       __syncwarp();  // tile `sidx` and the coefficients of sub-chunk sidx + 1 are in place
       if (prod) {
         live_nxt = rec.sub_live();
@@ -335,11 +413,13 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
       if (prod) rec.end_sub();
       live_cur = prod ? live_nxt : false;
     }
-    // ---- reduce the eight warps' partial tiles of this chunk and add to alm ----
-    double *fbuf = flush + (chk & 1) * K::FLUSH;
+    // ---- first the deferred reduction of the previous chunk, then park this chunk's partial tile ----
+    if (chk > 0) reduce_chunk(chk - 1, f_l_prev, f_sc_prev);
+    f_l_prev = f_l;
+    f_sc_prev = f_sc * f_fl;
     if (lane == 0) flags[(chk & 1) * NW + warp] = chunk_live ? 1 : 0;
     if (chunk_live) {
-      double *o = fbuf + warp * (K::C * FLS);
+      double *o = flush + (chk & 1) * K::FLUSH + warp * (K::C * FLS);
 #pragma unroll
       for (int p = 0; p < 2; ++p)
 #pragma unroll
@@ -351,35 +431,10 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
             d[FLS] = acc[p][sb][nb][1];
           }
     }
-    __syncthreads();
-    int lv[NW], any = 0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      lv[w] = flags[(chk & 1) * NW + w];
-      any |= lv[w];
-    }
-    if (any && f_l <= lmax) {
-#pragma unroll
-      for (int i = 0; i < NBLK; ++i) {
-        const int col = (threadIdx.x >> 5) + 8 * i;
-        int row, ri;
-        if (SPIN == 0) {
-          row = col >> 1;
-          ri = col & 1;
-        } else {
-          row = 2 * (col >> 2) + ((col >> 1) & 1);
-          ri = col & 1;
-        }
-        if (row < a.ncomp) {
-          double sum = 0.0;
-#pragma unroll
-          for (int w = 0; w < NW; ++w)
-            if (lv[w]) sum += fbuf[w * (K::C * FLS) + col * FLS + f_lidx];
-          atomicAdd(a.alm.p[row] + 2 * (cbase + f_l) + ri, sum * f_sc);
-        }
-      }
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(mbar + (chk & 1));
   }
+  reduce_chunk(st.nchunk - 1, f_l_prev, f_sc_prev);
   if (lane == 0 && a.work && n_rec > 0) {
     atomicAdd(a.work, n_rec * 32.0 * SL);
     atomicAdd(a.work + 1, n_acc * 32.0 * SL);
@@ -436,18 +491,20 @@ __global__ void __launch_bounds__(NT, 1) legendre_synthesis_kernel(LegArgs a) {
 
   // a_lm of one chunk: lane = l row.  Fetch into registers, convert and park in btile later.
   double2 av[K::NLOAD];
+  double sc_next = 0.0;
   auto fetch_alm = [&](int lstart) {
     const int l = lstart + lane;
+    sc_next = ldg_pin(a.scale + cbase + min(l, lmax));
 #pragma unroll
     for (int i = 0; i < K::NLOAD; ++i) {
       av[i] = make_double2(0., 0.);
       if (warp_alive && l <= lmax && i < a.ncomp)
-        av[i] = reinterpret_cast<const double2 *>(a.alm.p[i])[cbase + l];
+        av[i] = ldg_pin2(reinterpret_cast<const double2 *>(a.alm.p[i]) + cbase + l);
     }
   };
   auto park_alm = [&](int lstart) {
     const int l = lstart + lane;
-    const double sc = (warp_alive && l <= lmax) ? __ldg(a.scale + cbase + l) : 0.0;
+    const double sc = (warp_alive && l <= lmax) ? sc_next : 0.0;
     // step `lane` of the chunk has parity pb ^ (lane & 1), l index lane >> 1 within the parity
     double *row = btile + ((pb ^ (lane & 1)) * 16 + (lane >> 1)) * K::BSTR;
     if (SPIN == 0) {
@@ -469,7 +526,8 @@ __global__ void __launch_bounds__(NT, 1) legendre_synthesis_kernel(LegArgs a) {
   bool live_cur = false, live_nxt = false;
   // ---- prologue: sub-chunk 0 and the a_lm of chunk 0 ----
   fetch_alm(st.l0);
-  stage_coef<SPIN>(coefs, a, cbase, st.l0, lane);
+  park_coef(coefs, fetch_coef<SPIN>(a, cbase, st.l0, lane), lane);
+  double2 cnext = fetch_coef<SPIN>(a, cbase, st.l0 + SL, lane);  // coefficients of sub-chunk 1
   __syncwarp();
   if (warp_alive) {
     live_cur = rec.sub_live();
@@ -490,7 +548,10 @@ __global__ void __launch_bounds__(NT, 1) legendre_synthesis_kernel(LegArgs a) {
       const double *ccur = coefs + ((sidx + 1) & 1) * (SL * 2);
       const bool prod = warp_alive;  // one sub-chunk ahead, also past the end (see the analysis kernel)
       __syncwarp();
-      if (prod) stage_coef<SPIN>(coefs + ((sidx + 1) & 1) * (SL * 2), a, cbase, st.l0 + (sidx + 1) * SL, lane);
+      if (prod) {
+        park_coef(coefs + ((sidx + 1) & 1) * (SL * 2), cnext, lane);
+        cnext = fetch_coef<SPIN>(a, cbase, st.l0 + (sidx + 2) * SL, lane);
+      }
       __syncwarp();  // tile `sidx`, btile and the coefficients of sub-chunk sidx + 1 are in place
       if (prod) {
         live_nxt = rec.sub_live();

@@ -1,12 +1,13 @@
 """per-source-line and per-opcode summary of one kernel in an .ncu-rep (run where ncu is installed, no GPU needed)
-usage: ncu_lines.py report.ncu-rep [kernel-index] [top]"""
+usage: ncu_lines.py report.ncu-rep [kernel-name-regex] [top]"""
 import csv, subprocess, sys, io, collections
 rep = sys.argv[1]
-kid = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+kname = sys.argv[2] if len(sys.argv) > 2 else ""
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+ksel = ["--kernel-name", "regex:" + kname] if kname else []
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + ksel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, vals = rows[0], rows[2 + kid]
+hdr, vals = rows[0], rows[2]
 keys = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor_op_dmma.avg.pct_of_peak_sustained_active",
@@ -21,20 +22,14 @@ for h, v in zip(hdr, vals):
     short = h.split(".", 2)[-1] if h.startswith(("SM_", "TPC.")) else h
     if h in keys or short in keys or (h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio") and float(v or 0) > 0.15):
         print(f"{h:100s} {v:>18s}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + ksel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-# split per kernel: each kernel section starts with a "Function Name" row
-sections, cur = [], None
-for r in rows:
-    if r and r[0] == "Function Name":
-        cur = []
-        sections.append(cur)
-    if cur is not None:
-        cur.append(r)
-rows = sections[kid] if kid < len(sections) else rows
-hdr, line = None, None
+hdr, line, fname = None, None, ""
 lines, ops = {}, collections.defaultdict(lambda: [0, 0])
 for r in rows:
+    if r and r[0] == "File Path":
+        fname = r[1].split("/")[-1]
+        continue
     if r and r[0] == "Line No":
         hdr = r
         si, ii = hdr.index("# Samples"), hdr.index("Instructions Executed")
@@ -42,7 +37,7 @@ for r in rows:
     if not hdr or len(r) < 7:
         continue
     if r[0].isdigit():
-        line = int(r[0])
+        line = (fname, int(r[0]))
         lines.setdefault(line, [r[1], 0, 0, {}])
         continue
     if r[0] == "" and line is not None:
@@ -72,7 +67,7 @@ for d in lines.values():
 print("stall totals:", [(k[6:], v) for k, v in allst.most_common(8)])
 for ln, d in sorted(lines.items(), key=lambda x: -x[1][1])[:top]:
     st = sorted(d[3].items(), key=lambda x: -x[1])[:2]
-    print(f"{100 * d[1] / tot:5.1f}% inst {d[2] / 1e6:8.1f}M L{ln}: {d[0].strip()[:72]:72s} {[(k[6:], v) for k, v in st]}")
+    print(f"{100 * d[1] / tot:5.1f}% inst {d[2] / 1e6:8.1f}M {ln[0][:14]}:{ln[1]}: {d[0].strip()[:72]:72s} {[(k[6:], v) for k, v in st]}")
 ti = sum(v[0] for v in ops.values()) or 1
 print("opcodes:")
 for k, v in sorted(ops.items(), key=lambda x: -x[1][0])[:16]:
