@@ -51,7 +51,10 @@ SIGNATURES = {
     "hcu_map2alm": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_i64]),
     "hcu_map2alm_many": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "hcu_alm2map": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_i64]),
-    "hcu_map2phase": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
+    "hcu_legendre_batch_size": (c_int, [c_int]),
+    "hcu_map2phase": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_int, c_vp]),
+    "hcu_alm2phase": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_int, c_i64, c_i64, c_vp]),
+    "hcu_phase2map": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64]),
     "hcu_phase2alm": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_i64]),
     "hcu_alm2cl": (c_int, [c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_int, c_int, c_vp]),
     "hcu_last_sht_timing": (c_int, [c_vp, ctypes.POINTER(ctypes.c_float * 4)]),

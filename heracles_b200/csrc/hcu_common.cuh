@@ -134,9 +134,10 @@ int hcu_launch_map_values(hcu_ctx *ctx, i64 nside, int scheme, const double *lon
 int hcu_build_bluestein(hcu_ctx *ctx, hcu_geom *g);
 int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
                          const hcu_ptrs &maps, const double *ring_weights,
-                         i64 rp_lo, i64 rp_hi, double *phase);
+                         i64 rp_lo, i64 rp_hi, const int32_t *mlist, int nm, double *phase);
 int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
-                         const double *phase, const hcu_ptrs &maps);
+                         const double *phase, const int32_t *mpos, i64 rp_lo, i64 rp_hi,
+                         const hcu_ptrs &maps);
 int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c);
 int hcu_legendre_batch(int spin);  // components one Legendre launch can take: 12 (spin 0), 8 (spin 2)
 int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,

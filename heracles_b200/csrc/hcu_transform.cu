@@ -106,7 +106,7 @@ int analysis_pass(hcu_ctx *ctx, hcu_geom *g, hcu_coef *cf, int lmax, int spin, i
     HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_phase, sizeof(double) * 4 * (size_t)(lmax + 1) * nrp * nb));
     double *phase = (double *)ctx->ws_phase.ptr;
     StageTimer t0(ctx, 0, &ctx->sht_ms[0]);
-    HCU_CHECK(hcu_ring_fft_forward(ctx, g, lmax, nb, src, rw, 0, nrp, phase));
+    HCU_CHECK(hcu_ring_fft_forward(ctx, g, lmax, nb, src, rw, 0, nrp, nullptr, lmax + 1, phase));
     t0.stop();
     StageTimer t1(ctx, 2, &ctx->sht_ms[1]);
     HCU_CHECK(hcu_legendre_analysis(ctx, g, cf, lmax, spin, nb, phase, nullptr, lmax + 1, 0, nrp, fl, dst));
@@ -135,7 +135,7 @@ int synthesis_pass(hcu_ctx *ctx, hcu_geom *g, hcu_coef *cf, int lmax, int spin, 
     HCU_CHECK(hcu_legendre_synthesis(ctx, g, cf, lmax, spin, nb, src, nullptr, lmax + 1, 0, nrp, phase));
     t0.stop();
     StageTimer t1(ctx, 2, &ctx->sht_ms[3]);
-    HCU_CHECK(hcu_ring_fft_inverse(ctx, g, lmax, nb, phase, dst));
+    HCU_CHECK(hcu_ring_fft_inverse(ctx, g, lmax, nb, phase, nullptr, 0, nrp, dst));
     t1.stop();
     t0.collect();
     t1.collect();
@@ -293,14 +293,27 @@ extern "C" int hcu_alm2map(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int 
   return HCU_OK;
 }
 
+// ---- staged transform for the multi-GPU path ---------------------------------------------------
+namespace {
+int check_stage_args(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp, int64_t rp_lo,
+                     int64_t rp_hi, const int32_t *mlist, int nm) {
+  HCU_CHECK(check_sht_args(ctx, nside, lmax, spin, ncomp));
+  HCU_ARG(ncomp <= hcu_legendre_batch(spin), "at most 12 (spin 0) / 8 (spin 2) components per call");
+  HCU_ARG(0 <= rp_lo && rp_lo <= rp_hi && rp_hi <= 2 * nside, "ring pair range");
+  HCU_ARG(nm >= 0 && nm <= lmax + 1, "0 <= nm <= lmax + 1");
+  HCU_ARG(!mlist || hcu_dev_accessible(mlist), "mlist must be on the device");
+  return HCU_OK;
+}
+}  // namespace
+
+extern "C" int hcu_legendre_batch_size(int spin) { return hcu_legendre_batch(spin); }
+
 extern "C" int hcu_map2phase(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp,
                              const double *maps, int64_t map_stride,
                              const double *ring_weights, int64_t rp_lo, int64_t rp_hi,
-                             double *phase) {
-  HCU_CHECK(check_sht_args(ctx, nside, lmax, 0, ncomp));
+                             const int32_t *mlist, int nm, double *phase) {
+  HCU_CHECK(check_stage_args(ctx, nside, lmax, 0, ncomp, rp_lo, rp_hi, mlist, nm));
   HCU_ARG(maps && phase, "null pointer");
-  HCU_ARG(ncomp <= HCU_MAX_BATCH, "at most 10 components per call");
-  HCU_ARG(0 <= rp_lo && rp_lo <= rp_hi && rp_hi <= 2 * nside, "ring pair range");
   HCU_ARG(hcu_dev_accessible(maps) && hcu_dev_accessible(phase), "device pointers required");
   HCU_ARG(!ring_weights || hcu_dev_accessible(ring_weights), "ring_weights must be on the device");
   HCU_CUDA(cudaSetDevice(ctx->device));
@@ -309,19 +322,16 @@ extern "C" int hcu_map2phase(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp,
   hcu_ptrs src;
   for (int c = 0; c < HCU_MAX_BATCH; ++c)
     src.p[c] = c < ncomp ? const_cast<double *>(maps) + (i64)c * map_stride : nullptr;
-  return hcu_ring_fft_forward(ctx, g, lmax, ncomp, src, ring_weights, rp_lo, rp_hi, phase);
+  return hcu_ring_fft_forward(ctx, g, lmax, ncomp, src, ring_weights, rp_lo, rp_hi, mlist, nm, phase);
 }
 
 extern "C" int hcu_phase2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
                              const double *phase, const int32_t *mlist, int nm,
                              int64_t rp_lo, int64_t rp_hi, const double *fl, void *alm,
                              int64_t alm_stride) {
-  HCU_CHECK(check_sht_args(ctx, nside, lmax, spin, ncomp));
-  HCU_ARG(phase && alm && nm >= 0, "null pointer");
-  HCU_ARG(ncomp <= hcu_legendre_batch(spin), "at most 12 (spin 0) / 8 (spin 2) components per call");
-  HCU_ARG(0 <= rp_lo && rp_lo <= rp_hi && rp_hi <= 2 * nside, "ring pair range");
+  HCU_CHECK(check_stage_args(ctx, nside, lmax, spin, ncomp, rp_lo, rp_hi, mlist, nm));
+  HCU_ARG(phase && alm, "null pointer");
   HCU_ARG(hcu_dev_accessible(phase) && hcu_dev_accessible(alm), "device pointers required");
-  HCU_ARG(!mlist || hcu_dev_accessible(mlist), "mlist must be on the device");
   HCU_ARG(!fl || hcu_dev_accessible(fl), "fl must be on the device");
   HCU_CUDA(cudaSetDevice(ctx->device));
   hcu_geom *g;
@@ -332,4 +342,35 @@ extern "C" int hcu_phase2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, in
   for (int c = 0; c < HCU_MAX_BATCH; ++c)
     rows.p[c] = c < ncomp ? (double *)alm + 2 * (i64)c * alm_stride : nullptr;
   return hcu_legendre_analysis(ctx, g, cf, lmax, spin, ncomp, phase, mlist, nm, rp_lo, rp_hi, fl, rows);
+}
+
+extern "C" int hcu_alm2phase(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
+                             const void *alm, int64_t alm_stride, const int32_t *mlist, int nm,
+                             int64_t rp_lo, int64_t rp_hi, double *phase) {
+  HCU_CHECK(check_stage_args(ctx, nside, lmax, spin, ncomp, rp_lo, rp_hi, mlist, nm));
+  HCU_ARG(phase && alm, "null pointer");
+  HCU_ARG(hcu_dev_accessible(phase) && hcu_dev_accessible(alm), "device pointers required");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  hcu_geom *g;
+  hcu_coef *cf;
+  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
+  HCU_CHECK(hcu_get_coef(ctx, lmax, spin, &cf));
+  hcu_ptrs rows;
+  for (int c = 0; c < HCU_MAX_BATCH; ++c)
+    rows.p[c] = c < ncomp ? (double *)alm + 2 * (i64)c * alm_stride : nullptr;
+  return hcu_legendre_synthesis(ctx, g, cf, lmax, spin, ncomp, rows, mlist, nm, rp_lo, rp_hi, phase);
+}
+
+extern "C" int hcu_phase2map(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp, const double *phase,
+                             const int32_t *mpos, int64_t rp_lo, int64_t rp_hi, double *maps,
+                             int64_t map_stride) {
+  HCU_CHECK(check_stage_args(ctx, nside, lmax, 0, ncomp, rp_lo, rp_hi, mpos, 0));
+  HCU_ARG(maps && phase, "null pointer");
+  HCU_ARG(hcu_dev_accessible(maps) && hcu_dev_accessible(phase), "device pointers required");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  hcu_geom *g;
+  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
+  hcu_ptrs dst;
+  for (int c = 0; c < HCU_MAX_BATCH; ++c) dst.p[c] = c < ncomp ? maps + (i64)c * map_stride : nullptr;
+  return hcu_ring_fft_inverse(ctx, g, lmax, ncomp, phase, mpos, rp_lo, rp_hi, dst);
 }

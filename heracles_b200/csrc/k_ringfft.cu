@@ -158,13 +158,16 @@ __device__ __forceinline__ void store_phase(double *phase, i64 idx, double2 n,
   *o = make_double4(p.x, p.y, q.x, q.y);
 }
 
-// grid: (m blocks, cap ring pairs in range); one component per launch
-__global__ void cap_post_kernel(i64 nside, int lmax, int ncomp, int comp,
-                                const double2 *Yc, const double *ring_weights,
+// grid: (row blocks, cap ring pairs in range, components); row -> m through mlist (nullptr: identity)
+__global__ void cap_post_kernel(i64 nside, int nm, const int32_t *mlist, int ncomp,
+                                const double2 *Y, i64 ncap, const double *ring_weights,
                                 i64 rp_lo, i64 nrp_local, i64 rp_first,
                                 double *phase) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m > lmax) return;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nm) return;
+  const int m = mlist ? mlist[row] : row;
+  const int comp = blockIdx.z;
+  const double2 *Yc = Y + (i64)comp * ncap;
   const i64 rp = rp_first + blockIdx.y;
   const int i = (int)rp + 1;
   const int n = 4 * i;
@@ -181,17 +184,18 @@ __global__ void cap_post_kernel(i64 nside, int lmax, int ncomp, int comp,
              (12.0 * (double)nside * (double)nside);
   if (ring_weights) w *= ring_weights[rp];
   double2 ph = expmipi((double)m / (4.0 * (double)i));
-  i64 idx = ((i64)m * nrp_local + (rp - rp_lo)) * ncomp + comp;
+  i64 idx = ((i64)row * nrp_local + (rp - rp_lo)) * ncomp + comp;
   store_phase(phase, idx, xn, xs, ph, w);
 }
 
 // belt: X[rb][k], rb = ring - nside (0..2 nside), k = 0..2 nside
-__global__ void belt_post_kernel(i64 nside, int lmax, int ncomp, int comp,
+__global__ void belt_post_kernel(i64 nside, int nm, const int32_t *mlist, int ncomp, int comp,
                                  const double2 *X, const double *ring_weights,
                                  i64 rp_lo, i64 nrp_local, i64 rp_first,
                                  double *phase) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m > lmax) return;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nm) return;
+  const int m = mlist ? mlist[row] : row;
   const i64 rp = rp_first + blockIdx.y;
   const i64 i = rp + 1;  // north ring number, nside <= i <= 2 nside
   const int n4 = (int)(4 * nside);
@@ -212,39 +216,44 @@ __global__ void belt_post_kernel(i64 nside, int lmax, int ncomp, int comp,
   if (ring_weights) w *= ring_weights[rp];
   double2 ph = make_double2(1., 0.);
   if (((i - nside) & 1) == 0) ph = expmipi((double)m / (4.0 * (double)nside));
-  i64 idx = ((i64)m * nrp_local + (rp - rp_lo)) * ncomp + comp;
+  i64 idx = ((i64)row * nrp_local + (rp - rp_lo)) * ncomp + comp;
   store_phase(phase, idx, xn, xs, ph, w);
 }
 
 // ---------------------------------------------------------------------------
 // inverse direction (synthesis): phase (b_m per ring) -> ring pixels
-// phase layout for synthesis: phase[((m * nrp + rp) * ncomp + c) * 4] = (reN, imN, reS, imS)
+// phase layout for synthesis: phase[((row * nrp_local + rp - rp_lo) * ncomp + c) * 4] = (reN, imN, reS, imS),
+// row = mpos[m] (nullptr: row = m; negative: this m is absent)
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ int row_of(const int32_t *mpos, int m) { return mpos ? mpos[m] : m; }
 
-// belt: build the half-complex spectrum of each ring, then cuFFT Z2D
-__global__ void belt_pre_inv_kernel(i64 nside, int lmax, int ncomp, int comp,
-                                    const double *phase, double2 *X) {
+// belt: build the half-complex spectrum of the rings rb0 .. rb0 + gridDim.y - 1, then cuFFT Z2D
+__global__ void belt_pre_inv_kernel(i64 nside, int lmax, const int32_t *mpos, int ncomp, int comp,
+                                    const double *phase, i64 rp_lo, i64 nrp, i64 rb0, double2 *X) {
   const int n4 = (int)(4 * nside);
   const int nk = n4 / 2 + 1;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nk) return;
-  const i64 rb = blockIdx.y;  // 0..2 nside
+  const i64 rb = rb0 + blockIdx.y;  // 0..2 nside
   const i64 ring = rb + nside;
   const bool south = ring > 2 * nside;
-  const i64 rp = (south ? 4 * nside - ring : ring) - 1;
-  const i64 nrp = 2 * nside;
+  const i64 rp = (south ? 4 * nside - ring : ring) - 1 - rp_lo;
   const bool shifted = (((south ? 4 * nside - ring : ring) - nside) & 1) == 0;
   // G[k] = sum over m = k (mod n4) of c_m + sum over m = -k (mod n4), m>0, of conj(c_m)
   double2 g = make_double2(0., 0.);
   for (int m = k; m <= lmax; m += n4) {
-    const double *p = phase + (((i64)m * nrp + rp) * ncomp + comp) * 4 + (south ? 2 : 0);
+    const int row = row_of(mpos, m);
+    if (row < 0) continue;
+    const double *p = phase + (((i64)row * nrp + rp) * ncomp + comp) * 4 + (south ? 2 : 0);
     double2 c = make_double2(p[0], p[1]);
     if (shifted) c = cmulc(c, expmipi((double)m / (4.0 * (double)nside)));
     g = cadd(g, c);
   }
   for (int m = n4 - k; m <= lmax; m += n4) {
     if (m == 0) continue;
-    const double *p = phase + (((i64)m * nrp + rp) * ncomp + comp) * 4 + (south ? 2 : 0);
+    const int row = row_of(mpos, m);
+    if (row < 0) continue;
+    const double *p = phase + (((i64)row * nrp + rp) * ncomp + comp) * 4 + (south ? 2 : 0);
     double2 c = make_double2(p[0], p[1]);
     if (shifted) c = cmulc(c, expmipi((double)m / (4.0 * (double)nside)));
     g = cadd(g, make_double2(c.x, -c.y));
@@ -261,26 +270,29 @@ __global__ void belt_pre_inv_kernel(i64 nside, int lmax, int ncomp, int comp,
 //      [ e^{2 pi i q k'/n} sum_{s=0}^{3} Z[k' + s i] e^{2 pi i q s/4} ].
 // Step 1 (cap_pre_inv_kernel): fold the m <= lmax coefficients of one ring pair
 // onto the 4i frequencies, Z[k] = GN[k] + i GS[k]; grid (k blocks, cap ring pairs, comps).
-__global__ void cap_pre_inv_kernel(i64 nside, int lmax, int ncomp, const double *phase,
-                                   double2 *Z, i64 ncap) {
-  const int i = blockIdx.y + 1;
+__global__ void cap_pre_inv_kernel(i64 nside, int lmax, const int32_t *mpos, int ncomp, const double *phase,
+                                   i64 rp_lo, i64 nrp, i64 rp_first, double2 *Z, i64 ncap) {
+  const int i = (int)rp_first + blockIdx.y + 1;
   const int n = 4 * i;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int comp = blockIdx.z;
-  const i64 nrp = 2 * nside;
-  const i64 rp = i - 1;
+  const i64 rp = i - 1 - rp_lo;
   // G[k] folded from m = k (mod n) and, conjugated, from m = -k (mod n)
   double2 gn = make_double2(0., 0.), gs = make_double2(0., 0.);
   for (int m = k; m <= lmax; m += n) {
-    const double4 p = *reinterpret_cast<const double4 *>(phase + (((i64)m * nrp + rp) * ncomp + comp) * 4);
+    const int row = row_of(mpos, m);
+    if (row < 0) continue;
+    const double4 p = *reinterpret_cast<const double4 *>(phase + (((i64)row * nrp + rp) * ncomp + comp) * 4);
     double2 e = expmipi((double)m / (4.0 * (double)i));
     gn = cadd(gn, cmulc(make_double2(p.x, p.y), e));
     gs = cadd(gs, cmulc(make_double2(p.z, p.w), e));
   }
   for (int m = n - k; m <= lmax; m += n) {
     if (m == 0) continue;
-    const double4 p = *reinterpret_cast<const double4 *>(phase + (((i64)m * nrp + rp) * ncomp + comp) * 4);
+    const int row = row_of(mpos, m);
+    if (row < 0) continue;
+    const double4 p = *reinterpret_cast<const double4 *>(phase + (((i64)row * nrp + rp) * ncomp + comp) * 4);
     double2 e = expmipi((double)m / (4.0 * (double)i));
     double2 cn = cmulc(make_double2(p.x, p.y), e);
     double2 cs = cmulc(make_double2(p.z, p.w), e);
@@ -392,13 +404,14 @@ int hcu_build_bluestein(hcu_ctx *ctx, hcu_geom *g) {
   return HCU_OK;
 }
 
-static int get_belt_plan(hcu_ctx *ctx, std::map<i64, cufftHandle> &cache, i64 nside,
-                         bool inverse, cufftHandle *out) {
-  auto it = cache.find(nside);
+// cuFFT plan-many over `batch` consecutive belt rings (cached per nside, batch and direction)
+static int get_belt_plan(hcu_ctx *ctx, i64 nside, int batch, bool inverse, cufftHandle *out) {
+  auto &cache = inverse ? ctx->belt_plan_inv : ctx->belt_plan;
+  const i64 key = nside * (i64)(1 << 20) + batch;
+  auto it = cache.find(key);
   if (it == cache.end()) {
     cufftHandle plan;
     int n4 = (int)(4 * nside);
-    int batch = (int)(2 * nside + 1);
     HCU_CUFFT(cufftCreate(&plan));
     size_t ws = 0;
     if (!inverse)
@@ -407,25 +420,42 @@ static int get_belt_plan(hcu_ctx *ctx, std::map<i64, cufftHandle> &cache, i64 ns
     else
       HCU_CUFFT(cufftMakePlanMany(plan, 1, &n4, nullptr, 1, n4 / 2 + 1, nullptr, 1, n4,
                                   CUFFT_Z2D, batch, &ws));
-    cache[nside] = plan;
-    it = cache.find(nside);
+    cache[key] = plan;
+    it = cache.find(key);
   }
   HCU_CUFFT(cufftSetStream(it->second, ctx->stream));
   *out = it->second;
   return HCU_OK;
 }
 
-// forward ring FFT stage for ring pairs [rp_lo, rp_hi) of ncomp maps
+// the belt rings (rb = ring - nside) that ring pairs [belt_lo, belt_hi) touch: a northern run and its
+// southern mirror; they are merged into one run when they touch or overlap (blocks around the equator)
+static int belt_runs(i64 nside, i64 belt_lo, i64 belt_hi, i64 run0[2], i64 cnt[2]) {
+  const i64 n_lo = belt_lo + 1 - nside, n_hi = belt_hi - nside;          // north rb range, inclusive
+  i64 s_lo = 3 * nside - (belt_hi - 1) - 1, s_hi = 3 * nside - belt_lo - 1;  // south rb range, inclusive
+  if (s_lo <= n_hi + 1) {  // touching / overlapping at the equator (rb = nside)
+    run0[0] = n_lo;
+    cnt[0] = s_hi - n_lo + 1;
+    return 1;
+  }
+  run0[0] = n_lo; cnt[0] = n_hi - n_lo + 1;
+  run0[1] = s_lo; cnt[1] = s_hi - s_lo + 1;
+  return 2;
+}
+
+// forward ring FFT stage for ring pairs [rp_lo, rp_hi) of ncomp maps; phase rows follow mlist (nm rows)
 int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
                          const hcu_ptrs &maps, const double *ring_weights,
-                         i64 rp_lo, i64 rp_hi, double *phase) {
+                         i64 rp_lo, i64 rp_hi, const int32_t *mlist, int nm, double *phase) {
   const i64 nside = g->nside;
   const i64 ncap = 2 * nside * (nside - 1);
   const i64 nrp_local = rp_hi - rp_lo;
   const int n4 = (int)(4 * nside);
   const int nk = n4 / 2 + 1;
   const int mthreads = 128;
-  const unsigned mblocks = (unsigned)((lmax + 1 + mthreads - 1) / mthreads);
+  const unsigned mblocks = (unsigned)((nm + mthreads - 1) / mthreads);
+  (void)lmax;
+  if (nm <= 0 || nrp_local <= 0) return HCU_OK;
 
   // ---- polar caps: ring pairs rp < nside - 1 ---------------------------------
   i64 cap_lo = rp_lo, cap_hi = rp_hi < nside - 1 ? rp_hi : nside - 1;
@@ -447,53 +477,62 @@ int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
       HCU_LAUNCH_CHECK(ctx);
       i = ihi + 1;
     }
-    for (int c = 0; c < ncomp; ++c) {
-      dim3 grid(mblocks, (unsigned)(cap_hi - cap_lo));
-      cap_post_kernel<<<grid, mthreads, 0, ctx->stream>>>(
-          nside, lmax, ncomp, c, Y + (i64)c * ncap, ring_weights, rp_lo, nrp_local, cap_lo, phase);
-      HCU_LAUNCH_CHECK(ctx);
-    }
+    dim3 grid(mblocks, (unsigned)(cap_hi - cap_lo), (unsigned)ncomp);
+    cap_post_kernel<<<grid, mthreads, 0, ctx->stream>>>(nside, nm, mlist, ncomp, Y, ncap, ring_weights,
+                                                        rp_lo, nrp_local, cap_lo, phase);
+    HCU_LAUNCH_CHECK(ctx);
   }
 
   // ---- equatorial belt: ring pairs rp >= nside - 1 -------------------------------
   i64 belt_lo = rp_lo > nside - 1 ? rp_lo : nside - 1, belt_hi = rp_hi;
   if (belt_lo < belt_hi) {
-    cufftHandle plan;
-    HCU_CHECK(get_belt_plan(ctx, ctx->belt_plan, nside, false, &plan));
     HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_belt, sizeof(double2) * (size_t)nk * (2 * nside + 1)));
     double2 *X = (double2 *)ctx->ws_belt.ptr;
+    i64 run0[2], cnt[2];
+    const int nrun = belt_runs(nside, belt_lo, belt_hi, run0, cnt);
     for (int c = 0; c < ncomp; ++c) {
-      HCU_CUFFT(cufftExecD2Z(plan, maps.p[c] + ncap,
-                             reinterpret_cast<cufftDoubleComplex *>(X)));
-      ctx->n_cufft++;
+      for (int r = 0; r < nrun; ++r) {
+        cufftHandle plan;
+        HCU_CHECK(get_belt_plan(ctx, nside, (int)cnt[r], false, &plan));
+        HCU_CUFFT(cufftExecD2Z(plan, maps.p[c] + ncap + run0[r] * n4,
+                               reinterpret_cast<cufftDoubleComplex *>(X + run0[r] * nk)));
+        ctx->n_cufft++;
+      }
       dim3 grid(mblocks, (unsigned)(belt_hi - belt_lo));
       belt_post_kernel<<<grid, mthreads, 0, ctx->stream>>>(
-          nside, lmax, ncomp, c, X, ring_weights, rp_lo, nrp_local, belt_lo, phase);
+          nside, nm, mlist, ncomp, c, X, ring_weights, rp_lo, nrp_local, belt_lo, phase);
       HCU_LAUNCH_CHECK(ctx);
     }
   }
   return HCU_OK;
 }
 
-// inverse ring FFT stage (all ring pairs), phase rows are (reN, imN, reS, imS)
+// inverse ring FFT stage for ring pairs [rp_lo, rp_hi): phase rows are (reN, imN, reS, imS), the row of
+// m is mpos[m] (nullptr: m).  Only the pixels of those rings are written.
 int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
-                         const double *phase, const hcu_ptrs &maps) {
+                         const double *phase, const int32_t *mpos, i64 rp_lo, i64 rp_hi,
+                         const hcu_ptrs &maps) {
   const i64 nside = g->nside;
   const i64 ncap = 2 * nside * (nside - 1);
+  const i64 nrp_local = rp_hi - rp_lo;
   const int n4 = (int)(4 * nside);
   const int nk = n4 / 2 + 1;
+  if (nrp_local <= 0) return HCU_OK;
   // caps
-  if (nside > 1) {
+  i64 cap_lo = rp_lo, cap_hi = rp_hi < nside - 1 ? rp_hi : nside - 1;
+  if (cap_lo < cap_hi) {
     HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_cap, sizeof(double2) * (size_t)ncap * ncomp));
     double2 *Z = (double2 *)ctx->ws_cap.ptr;
-    dim3 pgrid((unsigned)((4 * (nside - 1) + 127) / 128), (unsigned)(nside - 1), (unsigned)ncomp);
-    cap_pre_inv_kernel<<<pgrid, 128, 0, ctx->stream>>>(nside, lmax, ncomp, phase, Z, ncap);
+    dim3 pgrid((unsigned)((4 * cap_hi + 127) / 128), (unsigned)(cap_hi - cap_lo), (unsigned)ncomp);
+    cap_pre_inv_kernel<<<pgrid, 128, 0, ctx->stream>>>(nside, lmax, mpos, ncomp, phase, rp_lo, nrp_local,
+                                                       cap_lo, Z, ncap);
     HCU_LAUNCH_CHECK(ctx);
-    int i = 1;
-    while (i < nside) {
+    int i = (int)cap_lo + 1;
+    const int iend = (int)cap_hi;
+    while (i <= iend) {
       int M = bluestein_M(i);
       int ihi = i;
-      while (ihi + 1 < nside && bluestein_M(ihi + 1) == M) ++ihi;
+      while (ihi + 1 <= iend && bluestein_M(ihi + 1) == M) ++ihi;
       size_t smem = (size_t)M * 24;
       HCU_CUDA(cudaFuncSetAttribute(cap_fft_inv_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -505,17 +544,25 @@ int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
     }
   }
   // belt
-  cufftHandle plan;
-  HCU_CHECK(get_belt_plan(ctx, ctx->belt_plan_inv, nside, true, &plan));
-  HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_belt, sizeof(double2) * (size_t)nk * (2 * nside + 1)));
-  double2 *X = (double2 *)ctx->ws_belt.ptr;
-  for (int c = 0; c < ncomp; ++c) {
-    dim3 grid((unsigned)((nk + 127) / 128), (unsigned)(2 * nside + 1));
-    belt_pre_inv_kernel<<<grid, 128, 0, ctx->stream>>>(nside, lmax, ncomp, c, phase, X);
-    HCU_LAUNCH_CHECK(ctx);
-    HCU_CUFFT(cufftExecZ2D(plan, reinterpret_cast<cufftDoubleComplex *>(X),
-                           maps.p[c] + ncap));
-    ctx->n_cufft++;
+  i64 belt_lo = rp_lo > nside - 1 ? rp_lo : nside - 1, belt_hi = rp_hi;
+  if (belt_lo < belt_hi) {
+    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_belt, sizeof(double2) * (size_t)nk * (2 * nside + 1)));
+    double2 *X = (double2 *)ctx->ws_belt.ptr;
+    i64 run0[2], cnt[2];
+    const int nrun = belt_runs(nside, belt_lo, belt_hi, run0, cnt);
+    for (int c = 0; c < ncomp; ++c) {
+      for (int r = 0; r < nrun; ++r) {
+        dim3 grid((unsigned)((nk + 127) / 128), (unsigned)cnt[r]);
+        belt_pre_inv_kernel<<<grid, 128, 0, ctx->stream>>>(nside, lmax, mpos, ncomp, c, phase, rp_lo,
+                                                           nrp_local, run0[r], X);
+        HCU_LAUNCH_CHECK(ctx);
+        cufftHandle plan;
+        HCU_CHECK(get_belt_plan(ctx, nside, (int)cnt[r], true, &plan));
+        HCU_CUFFT(cufftExecZ2D(plan, reinterpret_cast<cufftDoubleComplex *>(X + run0[r] * nk),
+                               maps.p[c] + ncap + run0[r] * n4));
+        ctx->n_cufft++;
+      }
+    }
   }
   return HCU_OK;
 }

@@ -1,0 +1,299 @@
+"""
+Multi-GPU catalogue -> Cl path: one process per GPU, ``torch.distributed`` for the plumbing.
+
+The reference is a single process (``heracles/mapping.py:130-174`` transforms the maps one
+after the other on the host), so there is no reference interface to mirror here; this module
+shards the SAME computation:
+
+1. catalogue pages are split over the ranks (``pages[rank::world]``); every rank builds full
+   partial maps with ``CudaHealpixMapper.map_values`` / ``hcu_map_values``;
+2. ``reduce_maps`` sums the partial maps over the ranks; afterwards rank g works on ITS block
+   of ring pairs only (a northern ring together with its southern mirror; blocks are balanced
+   by pixel count);
+3. ``DistributedTransform.map2alm``: local ring FFTs (``hcu_map2phase``) write the ring Fourier
+   coefficients ordered by destination rank, one ``all_to_all_single`` makes them
+   m-distributed (rank g owns m = g, g + world, ...: the Legendre work per m falls linearly in m,
+   so this interleaving balances it to within 2 world / lmax), the Legendre analysis
+   (``hcu_phase2alm``) runs per source block.  The Jacobi iterations of ``hp.map2alm``
+   (healpy's default ``iter=3``) run the same way backwards: ``hcu_alm2phase`` per destination
+   block, all-to-all, ``hcu_phase2map`` on the local rings, residual on the local pixels;
+4. every rank reduces the spectra of its own m (``hcu_alm2cl`` on alm that are zero for the
+   other m) and one ``all_reduce`` of ``nspec x (lmax + 1)`` doubles finishes the Cl.
+
+The exchange logic is backend agnostic: ``StagedKernels`` binds the four C-ABI stage functions
+for CUDA tensors; the CPU tests drive the same ``DistributedTransform`` over gloo with a
+stand-in that evaluates the stages with the oracle.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = ["ShardPlan", "StagedKernels", "DistributedTransform", "reduce_maps", "allreduce_cl"]
+
+
+# ---------------------------------------------------------------------------------------
+# the sharding plan (pure host logic)
+# ---------------------------------------------------------------------------------------
+class ShardPlan:
+    """which ring pairs and which m every rank owns"""
+
+    def __init__(self, nside: int, lmax: int, world: int):
+        if world < 1:
+            raise ValueError("world must be >= 1")
+        nrp = 2 * nside
+        if world > nrp:
+            raise ValueError("more ranks than ring pairs")
+        self.nside, self.lmax, self.world = int(nside), int(lmax), int(world)
+        self.npix = 12 * nside * nside
+        self.nalm = (lmax + 1) * (lmax + 2) // 2
+        self.nrp = nrp
+        # pixels per ring pair: caps 2 x 4i, belt 2 x 4 nside, the equator ring counts once
+        i = np.arange(1, nrp + 1, dtype=np.int64)
+        npair = np.where(i < nside, 8 * i, 8 * nside)
+        npair[-1] = 4 * nside
+        cum = np.concatenate([[0], np.cumsum(npair)])
+        bounds = [0]
+        for g in range(1, world):
+            target = cum[-1] * g / world
+            b = int(np.searchsorted(cum, target, side="left"))
+            b = max(b, bounds[-1] + 1)           # every block has at least one ring pair
+            b = min(b, nrp - (world - g))        # ... also the remaining ones
+            bounds.append(b)
+        bounds.append(nrp)
+        self.rp_bounds = bounds
+        # m owned by rank g: g, g + world, ...; the concatenation ordered by owner is the row order
+        # of every exchanged phase array
+        self.mlists = [np.arange(g, lmax + 1, world, dtype=np.int32) for g in range(world)]
+        self.m_all = np.concatenate(self.mlists).astype(np.int32)
+        self.m_off = np.concatenate([[0], np.cumsum([len(m) for m in self.mlists])]).astype(np.int64)
+        self.mpos = np.empty(lmax + 1, dtype=np.int32)
+        self.mpos[self.m_all] = np.arange(lmax + 1, dtype=np.int32)
+
+    # -- geometry -------------------------------------------------------------------------
+    def ring_start(self, i: int) -> int:
+        """first pixel of northern-hemisphere / belt ring i (1 <= i <= 2 nside + 1 as an end marker)"""
+        ns = self.nside
+        if i <= ns:
+            return 2 * i * (i - 1)
+        return 2 * ns * (ns - 1) + (i - ns) * 4 * ns
+
+    def rp_range(self, g: int) -> tuple[int, int]:
+        return self.rp_bounds[g], self.rp_bounds[g + 1]
+
+    def nrp_of(self, g: int) -> int:
+        return self.rp_bounds[g + 1] - self.rp_bounds[g]
+
+    def pixel_ranges(self, g: int) -> list[tuple[int, int]]:
+        """pixel index ranges (RING order) of the ring pairs of rank g: north run, south run"""
+        lo, hi = self.rp_range(g)
+        a, b = lo + 1, hi  # northern ring numbers a..b inclusive
+        n0, n1 = self.ring_start(a), self.ring_start(b + 1)
+        if b == 2 * self.nside:  # the block ends with the equator ring, which is its own mirror
+            return [(n0, self.npix - n0)]
+        return [(n0, n1), (self.npix - n1, self.npix - n0)]
+
+    def owner_of_m(self, m: int) -> int:
+        return m % self.world
+
+
+# ---------------------------------------------------------------------------------------
+# CUDA stage kernels through the C ABI
+# ---------------------------------------------------------------------------------------
+class StagedKernels:
+    """hcu_map2phase / hcu_phase2alm / hcu_alm2phase / hcu_phase2map on CUDA torch tensors"""
+
+    def __init__(self, ctx, nside: int, lmax: int):
+        self.ctx, self.nside, self.lmax = ctx, int(nside), int(lmax)
+        self.npix = 12 * nside * nside
+        self.nalm = (lmax + 1) * (lmax + 2) // 2
+
+    def batch_size(self, spin: int) -> int:
+        return int(self.ctx.lib.hcu_legendre_batch_size(int(spin)))
+
+    def _check(self, status):
+        if status != 0:
+            from . import _lib
+
+            _lib.check(status)
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else t.data_ptr()
+
+    def map2phase(self, maps, rp_lo, rp_hi, mlist, phase):
+        nb = maps.shape[0]
+        self._check(self.ctx.lib.hcu_map2phase(self.ctx.handle, self.nside, self.lmax, nb, maps.data_ptr(), maps.stride(0),
+                                               None, rp_lo, rp_hi, self._p(mlist), mlist.numel(), phase.data_ptr()))
+
+    def phase2alm(self, phase, spin, nb, mlist, rp_lo, rp_hi, alm):
+        self._check(self.ctx.lib.hcu_phase2alm(self.ctx.handle, self.nside, self.lmax, spin, nb, phase.data_ptr(),
+                                               self._p(mlist), mlist.numel(), rp_lo, rp_hi, None, alm.data_ptr(), alm.stride(0)))
+
+    def alm2phase(self, alm, spin, nb, mlist, rp_lo, rp_hi, phase):
+        self._check(self.ctx.lib.hcu_alm2phase(self.ctx.handle, self.nside, self.lmax, spin, nb, alm.data_ptr(), alm.stride(0),
+                                               self._p(mlist), mlist.numel(), rp_lo, rp_hi, phase.data_ptr()))
+
+    def phase2map(self, phase, nb, mpos, rp_lo, rp_hi, maps):
+        self._check(self.ctx.lib.hcu_phase2map(self.ctx.handle, self.nside, self.lmax, nb, phase.data_ptr(), self._p(mpos),
+                                               rp_lo, rp_hi, maps.data_ptr(), maps.stride(0)))
+
+    def sync_streams(self):
+        """make the library's stream the caller's current torch stream"""
+        import torch
+
+        # torch's default stream has handle 0, which hcu_set_stream reads as "the context's own
+        # stream": name the legacy default stream explicitly (cudaStreamLegacy = 1)
+        self.ctx.set_stream(torch.cuda.current_stream().cuda_stream or 1)
+
+
+# ---------------------------------------------------------------------------------------
+# the distributed transform
+# ---------------------------------------------------------------------------------------
+class DistributedTransform:
+    """
+    ``hp.map2alm`` (``heracles/healpy.py:183-189``) over the ranks of a process group.
+
+    maps : tensor ``[ncomp, npix]`` float64 in which at least the pixels of this rank's ring
+        block hold the (rank-summed) map; spin 2: rows are (Q, U) pairs.
+    alm  : tensor ``[ncomp, nalm]`` complex128; on return the entries whose m this rank owns
+        hold the result, every other entry is zero (so a SUM all-reduce gathers them).
+    """
+
+    def __init__(self, kernels, plan: ShardPlan, rank: int, group=None, niter: int = 3, device=None):
+        import torch
+
+        self.k, self.plan, self.rank, self.group, self.niter = kernels, plan, int(rank), group, int(niter)
+        self.device = device if device is not None else torch.device("cpu")
+        dev = self.device
+        self.mlist_me = torch.from_numpy(plan.mlists[rank].copy()).to(dev)
+        self.m_all = torch.from_numpy(plan.m_all.copy()).to(dev)
+        self.mpos = torch.from_numpy(plan.mpos.copy()).to(dev)
+        self._ws = {}
+        self.exchanged_bytes = 0
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _buf(self, name, n):
+        import torch
+
+        t = self._ws.get(name)
+        if t is None or t.numel() < n:
+            t = torch.empty(n, dtype=torch.float64, device=self.device)
+            self._ws[name] = t
+        return t[:n]
+
+    def release(self):
+        self._ws.clear()
+
+    def _all_to_all(self, out, inp, out_splits, in_splits):
+        import torch.distributed as dist
+
+        if self.plan.world == 1:
+            out.copy_(inp)
+            return
+        dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=self.group)
+        self.exchanged_bytes += 8 * (sum(in_splits) - in_splits[self.rank])
+
+    # -- one analysis pass over a batch: alm += A(maps) -------------------------------------------
+    def _analysis(self, maps, spin, alm):
+        plan, g, W = self.plan, self.rank, self.plan.world
+        nb = maps.shape[0]
+        lo, hi = plan.rp_range(g)
+        nrp_me, nm_me = hi - lo, len(plan.mlists[g])
+        per = nb * 4
+        send = self._buf("send", (plan.lmax + 1) * nrp_me * per)
+        self.k.map2phase(maps, lo, hi, self.m_all, send)
+        in_splits = [len(plan.mlists[d]) * nrp_me * per for d in range(W)]
+        out_splits = [nm_me * plan.nrp_of(s) * per for s in range(W)]
+        recv = self._buf("recv", sum(out_splits))
+        self._all_to_all(recv, send, out_splits, in_splits)
+        off = 0
+        for s in range(W):
+            slo, shi = plan.rp_range(s)
+            if nm_me and out_splits[s]:
+                self.k.phase2alm(recv[off:off + out_splits[s]], spin, nb, self.mlist_me, slo, shi, alm)
+            off += out_splits[s]
+
+    # -- one synthesis pass over a batch: maps (local rings) = S(alm) ------------------------------
+    def _synthesis(self, alm, spin, maps):
+        plan, g, W = self.plan, self.rank, self.plan.world
+        nb = alm.shape[0]
+        lo, hi = plan.rp_range(g)
+        nrp_me, nm_me = hi - lo, len(plan.mlists[g])
+        per = nb * 4
+        in_splits = [nm_me * plan.nrp_of(d) * per for d in range(W)]
+        out_splits = [len(plan.mlists[s]) * nrp_me * per for s in range(W)]
+        send = self._buf("send", sum(in_splits))
+        off = 0
+        for d in range(W):
+            dlo, dhi = plan.rp_range(d)
+            if nm_me and in_splits[d]:
+                self.k.alm2phase(alm, spin, nb, self.mlist_me, dlo, dhi, send[off:off + in_splits[d]])
+            off += in_splits[d]
+        recv = self._buf("recv", sum(out_splits))
+        self._all_to_all(recv, send, out_splits, in_splits)
+        # rows of recv are ordered by source rank = the order of plan.m_all
+        self.k.phase2map(recv, nb, self.mpos, lo, hi, maps)
+
+    # -- public -----------------------------------------------------------------------------------
+    def map2alm(self, maps, spin: int, alm, fl=None):
+        import torch
+
+        if spin not in (0, 2):
+            msg = f"spin-{spin} maps not yet supported"
+            raise NotImplementedError(msg)
+        plan = self.plan
+        ncomp = maps.shape[0]
+        if maps.shape[-1] != plan.npix or alm.shape != (ncomp, plan.nalm):
+            raise ValueError("maps / alm do not match the plan")
+        if spin == 2 and ncomp % 2:
+            raise ValueError("spin-2 input needs (Q, U) pairs")
+        cap = self.k.batch_size(spin)
+        ranges = plan.pixel_ranges(self.rank)
+        for c0 in range(0, ncomp, cap):
+            c1 = min(ncomp, c0 + cap)
+            mb, ab = maps[c0:c1], alm[c0:c1]
+            ab.zero_()
+            self._analysis(mb, spin, ab)
+            if self.niter > 0:
+                resid = self._buf("resid", (c1 - c0) * plan.npix).view(c1 - c0, plan.npix)
+                for _ in range(self.niter):
+                    self._synthesis(ab, spin, resid)
+                    for a, b in ranges:  # residual on the pixels of this rank's rings
+                        torch.sub(mb[:, a:b], resid[:, a:b], out=resid[:, a:b])
+                    self._analysis(resid, spin, ab)
+        if fl is not None:
+            alm.mul_(self._fl_full(fl))
+        return alm
+
+    def _fl_full(self, fl):
+        """fl[l] expanded to the alm layout (complex128 [nalm])"""
+        import torch
+
+        lmax = self.plan.lmax
+        key = ("fl", id(fl))
+        t = self._ws.get(key)
+        if t is None:
+            fl = np.asarray(fl, dtype=np.float64)
+            full = np.concatenate([fl[m:lmax + 1] for m in range(lmax + 1)])
+            t = torch.from_numpy(full).to(self.device).to(torch.complex128)
+            self._ws[key] = t
+        return t
+
+
+def reduce_maps(maps, group=None):
+    """sum the partial maps of all ranks (every rank gets the full sum)"""
+    import torch.distributed as dist
+
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(maps, group=group)
+    return maps
+
+
+def allreduce_cl(cl, group=None):
+    """Cl computed from m-distributed alm are partial sums over this rank's m"""
+    import torch.distributed as dist
+
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(cl, group=group)
+    return cl

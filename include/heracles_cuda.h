@@ -58,7 +58,8 @@ const char *hcu_last_error(void);
 int hcu_device_count(int *count);
 int hcu_create(int device, hcu_ctx **ctx);
 int hcu_destroy(hcu_ctx *ctx);
-/* use a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = the context's own */
+/* use a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = the context's own
+ * non-blocking stream.  To run on the legacy default stream pass cudaStreamLegacy ((void *)1). */
 int hcu_set_stream(hcu_ctx *ctx, void *cuda_stream);
 int hcu_synchronize(hcu_ctx *ctx);
 /* number of kernels of this library (and cuFFT executions) launched so far */
@@ -127,7 +128,7 @@ int hcu_map2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
 /* Same transform for rows that are NOT contiguous in memory: maps[c] / alm[c]
  * are per-row pointers.  This is what lets one call batch the maps of many
  * fields (heracles/mapping.py:151-171 transforms them one at a time) so that
- * the Legendre recursion is shared by up to 10 maps. */
+ * the Legendre recursion is shared by up to 12 maps (spin 0) / 4 fields (spin 2). */
 int hcu_map2alm_many(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
                      const double *const *maps, const double *ring_weights,
                      const double *pixel_weights, int niter, const double *fl,
@@ -139,24 +140,37 @@ int hcu_alm2map(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
                 int64_t map_stride);
 
 /* Staged transform for the multi-GPU path (no reference counterpart: the
- * reference is single process).  Ring pairs rp = 0..2 nside-1 (north ring
- * rp+1 with its southern mirror; rp = 2 nside - 1 is the equator).
- *   hcu_map2phase: ring FFT stage for ring pairs [rp_lo, rp_hi) of maps that
- *     hold AT LEAST those rings (full-size maps); writes
- *     phase[(m * nrp_local + (rp - rp_lo)) * ncomp + c] as 4 doubles
- *     (re+, im+, re-, im-) with +/- = north +/- south, already multiplied by
- *     the quadrature weight and exp(-i m phi0).
- *   hcu_phase2alm: Legendre stage for the m values mlist[0..nm) over ring
- *     pairs [rp_lo, rp_hi); phase is indexed by position in mlist;
- *     accumulates (+=) into alm at the global (l, m) positions. */
+ * reference is single process; these are the four halves of hp.map2alm /
+ * hp.alm2map, heracles/healpy.py:183-189, that heracles_b200/dist.py strings
+ * together with NCCL exchanges in between).  Ring pairs rp = 0..2 nside-1
+ * (north ring rp+1 with its southern mirror; rp = 2 nside - 1 is the equator).
+ * Device pointers only; asynchronous on the context's stream.
+ *   "phase" arrays are float64[nm][rp_hi - rp_lo][ncomp][4]; row r belongs to
+ *   m = mlist[r] (NULL: m = r).  Analysis direction: (re, im) of north+south and
+ *   north-south, multiplied by the quadrature weight and exp(-i m phi0).
+ *   Synthesis direction: (re, im) of the northern and of the southern ring.
+ *   hcu_map2phase  ring FFTs of ring pairs [rp_lo, rp_hi) of full-size maps.
+ *   hcu_phase2alm  Legendre analysis of those ring pairs for the listed m;
+ *                  ACCUMULATES (+=) into alm at the global (l, m) positions.
+ *   hcu_alm2phase  Legendre synthesis for the listed m on ring pairs [rp_lo, rp_hi).
+ *   hcu_phase2map  inverse ring FFTs; mpos[m] = row of m in phase (NULL: m,
+ *                  negative: absent); writes only the pixels of those rings.
+ * ncomp <= hcu_legendre_batch_size(spin) per call (12 for spin 0, 8 for spin 2). */
+int hcu_legendre_batch_size(int spin);
 int hcu_map2phase(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp,
                   const double *maps, int64_t map_stride,
                   const double *ring_weights, int64_t rp_lo, int64_t rp_hi,
-                  double *phase);
+                  const int32_t *mlist, int nm, double *phase);
 int hcu_phase2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
                   const double *phase, const int32_t *mlist, int nm,
                   int64_t rp_lo, int64_t rp_hi, const double *fl, void *alm,
                   int64_t alm_stride);
+int hcu_alm2phase(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
+                  const void *alm, int64_t alm_stride, const int32_t *mlist, int nm,
+                  int64_t rp_lo, int64_t rp_hi, double *phase);
+int hcu_phase2map(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp, const double *phase,
+                  const int32_t *mpos, int64_t rp_lo, int64_t rp_hi, double *maps,
+                  int64_t map_stride);
 
 /* ---- alm -> Cl ------------------------------------------------------------ */
 /* alm2cl(alm, alm2, lmax=lmax) -- heracles/twopoint.py:63-101, as a block:

@@ -36,7 +36,7 @@ def gpu_phase(ctx, nside, lmax, maps, rp_lo=0, rp_hi=None):
     dm.to_device()
     ph = DeviceArray.zeros(ctx, (lmax + 1, rp_hi - rp_lo, k, 4))
     _lib.check(
-        ctx.lib.hcu_map2phase(ctx.handle, nside, lmax, k, dm.device_ptr, maps.shape[1], None, rp_lo, rp_hi, ph.device_ptr)
+        ctx.lib.hcu_map2phase(ctx.handle, nside, lmax, k, dm.device_ptr, maps.shape[1], None, rp_lo, rp_hi, None, lmax + 1, ph.device_ptr)
     )
     ctx.synchronize()
     return np.array(ph._host(), copy=True)
