@@ -160,6 +160,14 @@ class Pipeline:
         self.pages = max(1, cfg["rows"] // PAGE_ROWS)
         self.page_rows = min(PAGE_ROWS, cfg["rows"])
         self.pool = min(POOL_PAGES, self.pages)
+        self.dist = None
+        if world > 1:
+            # ring-block / m-distributed transform over the ranks (heracles_b200/dist.py)
+            from heracles_b200.dist import DistributedTransform, ShardPlan, StagedKernels
+
+            self.plan = ShardPlan(nside, lmax, world)
+            self.kernels = StagedKernels(self.ctx, nside, lmax)
+            self.dist = DistributedTransform(self.kernels, self.plan, rank, niter=niter, device=torch.device("cuda"))
         self.make_catalogue()
 
     # synthetic catalogue: uniform positions, w ~ U(0.5,1.5), g ~ N(0,0.3)  
@@ -236,6 +244,11 @@ class Pipeline:
         calls = [(0, 0, nb)]
         if cfg["she"]:
             calls.append((2, nb, 2 * nb))
+        if self.dist is not None:
+            # every rank transforms its ring block / its m; alm rows are zero for foreign m
+            for spin, row0, n in calls:
+                self.dist.map2alm(self.maps[row0:row0 + n], spin, self.alm[row0:row0 + n])
+            return  # Legendre time and work are collected once per timed loop, see dist_stats()
         for spin, row0, n in calls:
             self.check(lib.hcu_map2alm(h, cfg["nside"], cfg["lmax"], spin, n, self.maps[row0].data_ptr(), self.npix,
                                        None, None, self.niter, None, self.alm[row0].data_ptr(), self.nalm))
@@ -244,13 +257,33 @@ class Pipeline:
             stats["fft_ms"] += ms[0] + ms[3]
             stats["leg_ana_ms"] += ms[1]
             stats["leg_syn_ms"] += ms[2]
-            # counters cover every analysis pass of the call; batches of <= 10 components
-            stats["leg_ana_flops"] += legendre_flops(spin, min(n, 10), rec, acc)
+            # counters cover every analysis pass of the call; the recursion is shared by the
+            # components of a batch (12 spin-0 maps / 4 spin-2 fields), so weight the batches
+            cap = 12 if spin == 0 else 8
+            nbat = -(-n // cap)
+            for i in range(nbat):
+                nc = min(cap, n - i * cap)
+                stats["leg_ana_flops"] += legendre_flops(spin, nc, rec / nbat, acc / nbat)
+
+    def dist_flops_per_cell(self):
+        """executed flops per accumulated cell-batch of one analysis pass, summed over the Legendre batches"""
+        nb, tot, nbat = self.nbins, 0.0, 0
+        for spin, n in ((0, nb), (2, 2 * nb if self.cfg["she"] else 0)):
+            cap = 12 if spin == 0 else 8
+            for i in range(-(-n // cap) if n else 0):
+                nc = min(cap, n - i * cap)
+                tot += legendre_flops(spin, nc, 1.0, 1.0)
+                nbat += 1
+        return tot, nbat
 
     def stage_cl(self):
         cfg = self.cfg
         self.check(self.lib.hcu_alm2cl(self.h, self.ncomp, self.alm.data_ptr(), self.nalm, cfg["lmax"], self.ncomp,
                                        self.alm.data_ptr(), self.nalm, cfg["lmax"], cfg["lmax"], self.cl.data_ptr()))
+        if self.world > 1:  # partial sums over this rank's m
+            import torch.distributed as dist
+
+            dist.all_reduce(self.cl)
 
     def check(self, status):
         if status != 0:
@@ -264,9 +297,9 @@ class Pipeline:
             ev[0].record()
             self.stage_map()
             ev[1].record()
-            self.stage_normalise()
             if self.world > 1:
                 self.reduce_maps()
+            self.stage_normalise()
             ev[2].record()
             self.stage_transform(stats)
             ev[3].record()
@@ -280,10 +313,10 @@ class Pipeline:
         return ev[0].elapsed_time(ev[4])
 
     def reduce_maps(self):
+        """partial maps of the ranks -> full maps (NCCL all-reduce on the pipeline's stream)"""
         import torch.distributed as dist
-        self.stream.synchronize()
+
         dist.all_reduce(self.maps)
-        self.torch.cuda.synchronize()
 
     # ---- end-to-end through the public API with pinned host pages ----
     def make_host_pool(self):
@@ -312,6 +345,7 @@ class Pipeline:
         t0 = time.perf_counter()
         maps = {}
         h2d = 0
+        dist_mode = self.world > 1
         vis = mapper.create()
         vis += 1.0
         for b in range(self.nbins):
@@ -328,13 +362,33 @@ class Pipeline:
                     h2d += 4 * rows * 8
             nbar, wbar = self.norm[b]
             pos /= nbar
-            pos -= vis
+            if not dist_mode:
+                pos -= vis
             maps["POS", b] = pos
             if she is not None:
                 she /= wbar
                 maps["SHE", b] = she
         bad = mapper.context.bad_rows()
         assert bad == 0
+        if dist_mode:
+            # partial maps of this rank's pages -> sum over ranks -> (once) the visibility subtraction
+            # -> ring-block / m-distributed transform -> Cl block on every rank
+            from heracles_b200.dist import DistributedPipeline
+
+            dp = DistributedPipeline(mapper)
+
+            def finish(stack, spin):
+                if spin == 0:
+                    stack.sub_(1.0)
+
+            cl = dp.spectra([maps["POS", b] for b in range(self.nbins)],
+                            [maps["SHE", b] for b in range(self.nbins)] if cfg["she"] else [], finish=finish)
+            host = cl.cpu().numpy()
+            d2h = host.nbytes
+            checksum = float(np.triu(host.sum(axis=-1)).sum())
+            ncl = self.ncomp * (self.ncomp + 1) // 2
+            dt = time.perf_counter() - t0
+            return dt, h2d, d2h, checksum, ncl
         alms = hb.transform(fields, maps)
         for (k, i), a in alms.items():
             hb.update_metadata(a, spin=0 if k == "POS" else 2)
@@ -487,6 +541,9 @@ def main():
     for _ in range(args.warmup):
         pipe.step(dict(stats))
     barrier()
+    if pipe.dist is not None:
+        pipe.kernels.timing = True
+        work0 = ctx.sht_work()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ctx.launch_count()
@@ -499,6 +556,19 @@ def main():
     barrier()
     clocks = sampler.stop()
     l1 = ctx.launch_count()
+    if pipe.dist is not None:
+        # the staged path: Legendre analysis time from CUDA events around hcu_phase2alm, executed cells
+        # from the kernels' work counters (equal shares for the batches of a pass)
+        stats["leg_ana_ms"] = pipe.kernels.analysis_ms()
+        pipe.kernels.timing = False
+        work1 = ctx.sht_work()
+        per_cell, nbat = pipe.dist_flops_per_cell()
+        rec, acc = (work1[0] - work0[0]) / nbat, (work1[1] - work0[1]) / nbat
+        nb = cfg["nbins"]
+        for spin, n in ((0, nb), (2, 2 * nb if cfg["she"] else 0)):
+            cap = 12 if spin == 0 else 8
+            for i in range(-(-n // cap) if n else 0):
+                stats["leg_ana_flops"] += legendre_flops(spin, min(cap, n - i * cap), rec, acc)
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -29,7 +29,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["ShardPlan", "StagedKernels", "DistributedTransform", "reduce_maps", "allreduce_cl"]
+__all__ = ["ShardPlan", "StagedKernels", "DistributedTransform", "reduce_maps", "allreduce_cl", "as_torch", "DistributedPipeline"]
 
 
 # ---------------------------------------------------------------------------------------
@@ -107,6 +107,17 @@ class StagedKernels:
         self.ctx, self.nside, self.lmax = ctx, int(nside), int(lmax)
         self.npix = 12 * nside * nside
         self.nalm = (lmax + 1) * (lmax + 2) // 2
+        self.timing = False      # record CUDA events around the Legendre analysis launches
+        self._events = []
+
+    def analysis_ms(self) -> float:
+        """device milliseconds of the hcu_phase2alm launches since the last call (synchronises)"""
+        import torch
+
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self._events)
+        self._events = []
+        return ms
 
     def batch_size(self, spin: int) -> int:
         return int(self.ctx.lib.hcu_legendre_batch_size(int(spin)))
@@ -127,8 +138,16 @@ class StagedKernels:
                                                None, rp_lo, rp_hi, self._p(mlist), mlist.numel(), phase.data_ptr()))
 
     def phase2alm(self, phase, spin, nb, mlist, rp_lo, rp_hi, alm):
+        if self.timing:
+            import torch
+
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         self._check(self.ctx.lib.hcu_phase2alm(self.ctx.handle, self.nside, self.lmax, spin, nb, phase.data_ptr(),
                                                self._p(mlist), mlist.numel(), rp_lo, rp_hi, None, alm.data_ptr(), alm.stride(0)))
+        if self.timing:
+            e1.record()
+            self._events.append((e0, e1))
 
     def alm2phase(self, alm, spin, nb, mlist, rp_lo, rp_hi, phase):
         self._check(self.ctx.lib.hcu_alm2phase(self.ctx.handle, self.nside, self.lmax, spin, nb, alm.data_ptr(), alm.stride(0),
@@ -297,3 +316,84 @@ def allreduce_cl(cl, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(cl, group=group)
     return cl
+
+
+# ---------------------------------------------------------------------------------------
+# public multi-GPU entry point on top of CudaHealpixMapper
+# ---------------------------------------------------------------------------------------
+class _CudaView:
+    """exposes a raw device pointer through __cuda_array_interface__ (zero-copy torch view)"""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 3, "strides": None}
+
+
+def as_torch(arr, device):
+    """torch view of a contiguous ``DeviceArray`` (the managed memory ``Mapper.create()`` returns)"""
+    import torch
+
+    ptr = getattr(arr, "device_ptr", None)
+    if ptr is None:
+        return torch.as_tensor(np.ascontiguousarray(arr)).to(device)
+    return torch.as_tensor(_CudaView(ptr, arr.shape, arr.dtype.str), device=device)
+
+
+class DistributedPipeline:
+    """
+    Maps of one ``CudaHealpixMapper`` (every rank mapped ITS pages into them) -> angular power
+    spectra over all ranks.  ``spectra(pos_maps, she_maps)`` takes the lists of partial maps
+    (``(npix,)`` arrays for spin 0, ``(2, npix)`` for spin 2), sums them over the ranks, applies
+    ``finish(stack, spin)`` (e.g. the visibility subtraction that must happen once, after the
+    sum), transforms them m-distributed and returns the full ``[ncomp, ncomp, lmax + 1]`` block
+    of component spectra on every rank (rows: spin-0 maps first, then (E, B) per spin-2 field).
+    """
+
+    def __init__(self, mapper, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.mapper, self.group = mapper, group
+        self.ctx = mapper.context
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device("cuda", self.ctx.device)
+        self.plan = ShardPlan(mapper.nside, mapper.lmax, self.world)
+        self.kernels = StagedKernels(self.ctx, mapper.nside, mapper.lmax)
+        self.transform = DistributedTransform(self.kernels, self.plan, self.rank, group=group, niter=mapper.niter, device=self.device)
+
+    def alms(self, maps, spin, finish=None):
+        """list of partial maps of one spin -> m-distributed alm tensor [rows, nalm]"""
+        import torch
+
+        self.kernels.sync_streams()
+        plan = self.plan
+        rows = len(maps) * (1 if spin == 0 else 2)
+        stack = torch.empty(rows, plan.npix, dtype=torch.float64, device=self.device)
+        for i, m in enumerate(maps):
+            if hasattr(m, "to_device"):
+                m.to_device()
+            src = as_torch(m, self.device).reshape(-1, plan.npix)
+            stack[i * src.shape[0]:(i + 1) * src.shape[0]].copy_(src)
+        reduce_maps(stack, self.group)
+        if finish is not None:
+            finish(stack, spin)
+        alm = torch.zeros(rows, plan.nalm, dtype=torch.complex128, device=self.device)
+        fl = self.mapper._fl(spin)
+        self.transform.map2alm(stack, spin, alm, fl=fl)
+        return alm
+
+    def spectra(self, pos_maps=(), she_maps=(), finish=None):
+        import torch
+
+        parts = []
+        if len(pos_maps):
+            parts.append(self.alms(list(pos_maps), 0, finish))
+        if len(she_maps):
+            parts.append(self.alms(list(she_maps), 2, finish))
+        alm = torch.cat(parts) if len(parts) > 1 else parts[0]
+        n, lmax = alm.shape[0], self.plan.lmax
+        cl = torch.zeros(n, n, lmax + 1, dtype=torch.float64, device=self.device)
+        self.kernels._check(self.ctx.lib.hcu_alm2cl(self.ctx.handle, n, alm.data_ptr(), alm.stride(0), lmax, n, alm.data_ptr(),
+                                                    alm.stride(0), lmax, lmax, cl.data_ptr()))
+        allreduce_cl(cl, self.group)
+        return cl
