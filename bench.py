@@ -320,17 +320,26 @@ class Pipeline:
 
     # ---- end-to-end through the public API with pinned host pages ----
     def make_host_pool(self):
+        """pinned host copies of the catalogue pages THIS rank maps (pool index -> row of the host arrays)"""
         torch = self.torch
+        needed = sorted({p % self.pool for p in self.my_pages()})
+        self.hidx = {pi: j for j, pi in enumerate(needed)}
+        sel = torch.tensor(needed, device="cuda")
         self.hcat = []
         for b in range(self.nbins):
             c = self.cat[b]
             hc = {}
             for k, v in c.items():
+                v = v.view(self.pool, -1, self.page_rows) if k == "wg" else v.view(self.pool, self.page_rows)
+                v = v.index_select(0, sel)
                 t = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
                 t.copy_(v)
                 hc[k] = t.numpy()
             self.hcat.append(hc)
         torch.cuda.synchronize()
+        self.cat = None  # the device-resident catalogue is not needed by the end-to-end arm
+        if self.dist is not None:
+            self.dist.release()
 
     def e2e_step(self):
         hb = self.hb
@@ -353,12 +362,12 @@ class Pipeline:
             pos = mapper.create(spin=0)
             she = mapper.create(2, spin=2) if cfg["she"] else None
             for p in self.my_pages():
-                s = (p % self.pool) * rows
-                lon, lat, w = hc["lon"][s:s + rows], hc["lat"][s:s + rows], hc["w"][s:s + rows]
+                j = self.hidx[p % self.pool]
+                lon, lat, w = hc["lon"][j], hc["lat"][j], hc["w"][j]
                 mapper.map_values(lon, lat, pos, w, spin=0)
                 h2d += 3 * rows * 8
                 if she is not None:
-                    mapper.map_values(lon, lat, she, hc["wg"][p % self.pool], spin=2)
+                    mapper.map_values(lon, lat, she, hc["wg"][j], spin=2)
                     h2d += 4 * rows * 8
             nbar, wbar = self.norm[b]
             pos /= nbar
@@ -620,6 +629,8 @@ def main():
     }
 
     # end to end through the plugin API, host pages
+    if rank == 0:
+        print("device-resident arm: " + json.dumps({k: line[k] for k in ("value", "n_gpus", "stage_ms_per_step")}), file=sys.stderr, flush=True)
     if not args.no_e2e:
         pipe.make_host_pool()
         del pipe.maps, pipe.alm, pipe.cl
@@ -637,9 +648,11 @@ def main():
             t = torch.tensor([tt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             tt = float(t.item())
+        api = ("CudaHealpixMapper.map_values(sync=False) + heracles_b200.dist.DistributedPipeline.spectra, pinned host pages"
+               if world > 1 else
+               "CudaHealpixMapper.map_values(sync=False) + heracles_b200.transform + angular_power_spectra, pinned host pages")
         line["e2e"] = {"value": tt / max(1, args.e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(res[1]),
-                       "d2h_bytes_per_step": int(res[2]), "spectra": res[4], "checksum": res[3],
-                       "api": "CudaHealpixMapper.map_values(sync=False) + heracles_b200.transform + angular_power_spectra, pinned host pages"}
+                       "d2h_bytes_per_step": int(res[2]), "spectra": res[4], "checksum": res[3], "api": api}
 
     if rank == 0 and not args.no_cpu:
         _, info = cpu_sample(cfg, args.niter)
