@@ -355,8 +355,15 @@ class Pipeline:
         maps = {}
         h2d = 0
         dist_mode = self.world > 1
-        vis = mapper.create()
-        vis += 1.0
+        dp = None
+        if dist_mode:
+            # maps go bin by bin into device-resident stacks; the managed maps are freed right away
+            from heracles_b200.dist import DistributedPipeline
+
+            dp = DistributedPipeline(mapper, self.nbins, self.nbins if cfg["she"] else 0)
+        else:
+            vis = mapper.create()
+            vis += 1.0
         for b in range(self.nbins):
             hc = self.hcat[b]
             pos = mapper.create(spin=0)
@@ -371,27 +378,28 @@ class Pipeline:
                     h2d += 4 * rows * 8
             nbar, wbar = self.norm[b]
             pos /= nbar
-            if not dist_mode:
-                pos -= vis
-            maps["POS", b] = pos
             if she is not None:
                 she /= wbar
+            if dist_mode:
+                dp.put(0, b, pos)
+                if she is not None:
+                    dp.put(2, b, she)
+                del pos, she
+                continue
+            pos -= vis
+            maps["POS", b] = pos
+            if she is not None:
                 maps["SHE", b] = she
         bad = mapper.context.bad_rows()
         assert bad == 0
         if dist_mode:
             # partial maps of this rank's pages -> sum over ranks -> (once) the visibility subtraction
             # -> ring-block / m-distributed transform -> Cl block on every rank
-            from heracles_b200.dist import DistributedPipeline
-
-            dp = DistributedPipeline(mapper)
-
             def finish(stack, spin):
                 if spin == 0:
                     stack.sub_(1.0)
 
-            cl = dp.spectra([maps["POS", b] for b in range(self.nbins)],
-                            [maps["SHE", b] for b in range(self.nbins)] if cfg["she"] else [], finish=finish)
+            cl = dp.spectra(finish=finish)
             host = cl.cpu().numpy()
             d2h = host.nbytes
             checksum = float(np.triu(host.sum(axis=-1)).sum())

@@ -38,7 +38,10 @@ __all__ = ["ShardPlan", "StagedKernels", "DistributedTransform", "reduce_maps", 
 class ShardPlan:
     """which ring pairs and which m every rank owns"""
 
-    def __init__(self, nside: int, lmax: int, world: int):
+    def __init__(self, nside: int, lmax: int, world: int, cap_weight: float = 3.0):
+        """cap_weight: cost of a polar-cap pixel relative to a belt pixel in the ring FFT stage (the
+        caps' Bluestein FFTs cost about three times cuFFT's power-of-two belt transforms per pixel);
+        the ring-pair blocks are balanced by this weighted pixel count."""
         if world < 1:
             raise ValueError("world must be >= 1")
         nrp = 2 * nside
@@ -50,7 +53,7 @@ class ShardPlan:
         self.nrp = nrp
         # pixels per ring pair: caps 2 x 4i, belt 2 x 4 nside, the equator ring counts once
         i = np.arange(1, nrp + 1, dtype=np.int64)
-        npair = np.where(i < nside, 8 * i, 8 * nside)
+        npair = np.where(i < nside, 8 * i * float(cap_weight), 8.0 * nside)
         npair[-1] = 4 * nside
         cum = np.concatenate([[0], np.cumsum(npair)])
         bounds = [0]
@@ -341,14 +344,21 @@ def as_torch(arr, device):
 class DistributedPipeline:
     """
     Maps of one ``CudaHealpixMapper`` (every rank mapped ITS pages into them) -> angular power
-    spectra over all ranks.  ``spectra(pos_maps, she_maps)`` takes the lists of partial maps
-    (``(npix,)`` arrays for spin 0, ``(2, npix)`` for spin 2), sums them over the ranks, applies
-    ``finish(stack, spin)`` (e.g. the visibility subtraction that must happen once, after the
-    sum), transforms them m-distributed and returns the full ``[ncomp, ncomp, lmax + 1]`` block
-    of component spectra on every rank (rows: spin-0 maps first, then (E, B) per spin-2 field).
+    spectra over all ranks.
+
+        dp = DistributedPipeline(mapper, npos, nshe)
+        dp.put(0, i, pos_map)          # (npix,)   partial spin-0 map i of this rank
+        dp.put(2, i, she_map)          # (2, npix) partial spin-2 map i of this rank
+        cl = dp.spectra(finish=...)    # [ncomp, ncomp, lmax + 1] on every rank
+
+    ``put`` copies the (managed-memory) map into a device-resident stack, so the caller can free
+    it right away; ``spectra`` sums the stacks over the ranks, applies ``finish(stack, spin)``
+    (e.g. the visibility subtraction, which must happen once, after the sum), transforms them
+    ring-block / m-distributed and reduces the component spectra (rows: spin-0 maps first, then
+    (E, B) per spin-2 field; only the upper triangle j >= i is filled).
     """
 
-    def __init__(self, mapper, group=None):
+    def __init__(self, mapper, npos: int = 0, nshe: int = 0, group=None):
         import torch
         import torch.distributed as dist
 
@@ -360,36 +370,39 @@ class DistributedPipeline:
         self.plan = ShardPlan(mapper.nside, mapper.lmax, self.world)
         self.kernels = StagedKernels(self.ctx, mapper.nside, mapper.lmax)
         self.transform = DistributedTransform(self.kernels, self.plan, self.rank, group=group, niter=mapper.niter, device=self.device)
+        self.stacks = {}
+        if npos:
+            self.stacks[0] = torch.zeros(npos, self.plan.npix, dtype=torch.float64, device=self.device)
+        if nshe:
+            self.stacks[2] = torch.zeros(2 * nshe, self.plan.npix, dtype=torch.float64, device=self.device)
 
-    def alms(self, maps, spin, finish=None):
-        """list of partial maps of one spin -> m-distributed alm tensor [rows, nalm]"""
+    def put(self, spin: int, index: int, m) -> None:
+        """copy partial map ``index`` of the given spin into the device stack"""
+        self.kernels.sync_streams()
+        if hasattr(m, "to_device"):
+            m.to_device()
+        src = as_torch(m, self.device).reshape(-1, self.plan.npix)
+        n = src.shape[0]
+        self.stacks[spin][index * n:(index + 1) * n].copy_(src)
+        self.ctx.synchronize()  # the source may be freed by the caller
+
+    def alms(self, spin, finish=None):
+        """stack of one spin -> m-distributed alm tensor [rows, nalm]"""
         import torch
 
         self.kernels.sync_streams()
-        plan = self.plan
-        rows = len(maps) * (1 if spin == 0 else 2)
-        stack = torch.empty(rows, plan.npix, dtype=torch.float64, device=self.device)
-        for i, m in enumerate(maps):
-            if hasattr(m, "to_device"):
-                m.to_device()
-            src = as_torch(m, self.device).reshape(-1, plan.npix)
-            stack[i * src.shape[0]:(i + 1) * src.shape[0]].copy_(src)
+        stack = self.stacks[spin]
         reduce_maps(stack, self.group)
         if finish is not None:
             finish(stack, spin)
-        alm = torch.zeros(rows, plan.nalm, dtype=torch.complex128, device=self.device)
-        fl = self.mapper._fl(spin)
-        self.transform.map2alm(stack, spin, alm, fl=fl)
+        alm = torch.zeros(stack.shape[0], self.plan.nalm, dtype=torch.complex128, device=self.device)
+        self.transform.map2alm(stack, spin, alm, fl=self.mapper._fl(spin))
         return alm
 
-    def spectra(self, pos_maps=(), she_maps=(), finish=None):
+    def spectra(self, finish=None):
         import torch
 
-        parts = []
-        if len(pos_maps):
-            parts.append(self.alms(list(pos_maps), 0, finish))
-        if len(she_maps):
-            parts.append(self.alms(list(she_maps), 2, finish))
+        parts = [self.alms(spin, finish) for spin in (0, 2) if spin in self.stacks]
         alm = torch.cat(parts) if len(parts) > 1 else parts[0]
         n, lmax = alm.shape[0], self.plan.lmax
         cl = torch.zeros(n, n, lmax + 1, dtype=torch.float64, device=self.device)

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_shard_plan(nside, lmax, world):
     from heracles_b200.dist import ShardPlan
 
-    plan = ShardPlan(nside, lmax, world)
+    plan = ShardPlan(nside, lmax, world, cap_weight=1.0)
     assert plan.rp_bounds[0] == 0 and plan.rp_bounds[-1] == 2 * nside
     assert all(b > a for a, b in zip(plan.rp_bounds, plan.rp_bounds[1:]))
     # pixel ranges of the blocks tile the map exactly once
@@ -26,6 +26,12 @@ def test_shard_plan(nside, lmax, world):
     # blocks are balanced by pixel count
     sizes = [sum(b - a for a, b in plan.pixel_ranges(g)) for g in range(world)]
     assert max(sizes) - min(sizes) <= 16 * nside + 8 * nside
+    # the default plan weights cap pixels (slower FFTs): polar blocks get fewer pixels, still a tiling
+    wplan = ShardPlan(nside, lmax, world)
+    wr = sorted(r for g in range(world) for r in wplan.pixel_ranges(g))
+    assert wr[0][0] == 0 and wr[-1][1] == wplan.npix and all(a[1] == b[0] for a, b in zip(wr, wr[1:]))
+    if world > 1 and nside >= 64:
+        assert sum(b - a for a, b in wplan.pixel_ranges(0)) < sizes[0]
     # every m has exactly one owner and the row order is the concatenation of the owners' lists
     assert sorted(plan.m_all.tolist()) == list(range(lmax + 1))
     assert all(plan.owner_of_m(int(m)) == g for g in range(world) for m in plan.mlists[g])

@@ -31,17 +31,17 @@ full_pos = rng.standard_normal((npos, npix))
 full_she = rng.standard_normal((nshe, 2, npix))
 # every rank holds a share of the maps; the shares sum to the full maps
 share = (rank + 1) / (world * (world + 1) / 2)
-pos, she = [], []
+dp = DistributedPipeline(mapper, npos, nshe)
 for i in range(npos):
     m = mapper.create(spin=0)
     m[:] = full_pos[i] * share
-    pos.append(m)
+    dp.put(0, i, m)
 for i in range(nshe):
     m = mapper.create(2, spin=2)
     m[:] = full_she[i] * share
-    she.append(m)
-dp = DistributedPipeline(mapper)
-cl = dp.spectra(pos, she).cpu().numpy()
+    dp.put(2, i, m)
+del m
+cl = dp.spectra().cpu().numpy()
 torch.cuda.synchronize()
 ok = True
 if rank == 0:
