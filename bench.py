@@ -560,6 +560,7 @@ def main():
     barrier()
     if pipe.dist is not None:
         pipe.kernels.timing = True
+        pipe.dist.timing = True
         work0 = ctx.sht_work()
     sampler = ClockSampler(local)
     sampler.start()
@@ -578,6 +579,16 @@ def main():
         # from the kernels' work counters (equal shares for the batches of a pass)
         stats["leg_ana_ms"] = pipe.kernels.analysis_ms()
         pipe.kernels.timing = False
+        # per-rank stage times of the distributed transform (a2a includes waiting for the slowest rank)
+        st = pipe.dist.stage_ms()
+        pipe.dist.timing = False
+        names = ["fft", "a2a", "leg_ana", "leg_syn", "ifft"]
+        t = torch.tensor([st.get(k, 0.0) for k in names], device="cuda", dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        dist_stage = {k: [round(float(a[i]) / args.steps, 1) for a in allt] for i, k in enumerate(names)}
+        stats["fft_ms"] = st.get("fft", 0.0) + st.get("ifft", 0.0)
+        stats["leg_syn_ms"] = st.get("leg_syn", 0.0)
         work1 = ctx.sht_work()
         per_cell, nbat = pipe.dist_flops_per_cell()
         rec, acc = (work1[0] - work0[0]) / nbat, (work1[1] - work0[1]) / nbat
@@ -635,6 +646,8 @@ def main():
         "gpu_launches_detail": {"own_kernels": int(l1[0] - l0[0]), "cufft_execs": int(l1[1] - l0[1])},
         "clocks": clocks, "checksum": checksum,
     }
+    if pipe.dist is not None:
+        line["dist_stage_ms_per_rank"] = dist_stage
 
     # end to end through the plugin API, host pages
     if rank == 0:

@@ -54,6 +54,8 @@ SIGNATURES = {
     "hcu_legendre_batch_size": (c_int, [c_int]),
     "hcu_map2phase": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_int, c_vp]),
     "hcu_alm2phase": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_int, c_i64, c_i64, c_vp]),
+    "hcu_phase2alm_blocks": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64]),
+    "hcu_alm2phase_blocks": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp]),
     "hcu_phase2map": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64]),
     "hcu_phase2alm": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_i64]),
     "hcu_alm2cl": (c_int, [c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_int, c_int, c_vp]),

@@ -142,11 +142,11 @@ int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c);
 int hcu_legendre_batch(int spin);  // components one Legendre launch can take: 12 (spin 0), 8 (spin 2)
 int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
                           int spin, int ncomp, const double *phase,
-                          const int32_t *mlist_dev, int nm, i64 rp_lo, i64 rp_hi,
+                          const int32_t *mlist_dev, int nm, int nblk, const i64 *rp_bounds,
                           const double *fl_dev, const hcu_ptrs &alm);
 int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
                            int spin, int ncomp, const hcu_ptrs &alm,
-                           const int32_t *mlist_dev, int nm, i64 rp_lo, i64 rp_hi,
+                           const int32_t *mlist_dev, int nm, int nblk, const i64 *rp_bounds,
                            double *phase);
 
 static inline int ilog2_host(i64 v) {

@@ -109,7 +109,8 @@ int analysis_pass(hcu_ctx *ctx, hcu_geom *g, hcu_coef *cf, int lmax, int spin, i
     HCU_CHECK(hcu_ring_fft_forward(ctx, g, lmax, nb, src, rw, 0, nrp, nullptr, lmax + 1, phase));
     t0.stop();
     StageTimer t1(ctx, 2, &ctx->sht_ms[1]);
-    HCU_CHECK(hcu_legendre_analysis(ctx, g, cf, lmax, spin, nb, phase, nullptr, lmax + 1, 0, nrp, fl, dst));
+    const i64 full[2] = {0, nrp};
+    HCU_CHECK(hcu_legendre_analysis(ctx, g, cf, lmax, spin, nb, phase, nullptr, lmax + 1, 1, full, fl, dst));
     t1.stop();
     t0.collect();
     t1.collect();
@@ -132,7 +133,8 @@ int synthesis_pass(hcu_ctx *ctx, hcu_geom *g, hcu_coef *cf, int lmax, int spin, 
     HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_phase, sizeof(double) * 4 * (size_t)(lmax + 1) * nrp * nb));
     double *phase = (double *)ctx->ws_phase.ptr;
     StageTimer t0(ctx, 0, &ctx->sht_ms[2]);
-    HCU_CHECK(hcu_legendre_synthesis(ctx, g, cf, lmax, spin, nb, src, nullptr, lmax + 1, 0, nrp, phase));
+    const i64 full[2] = {0, nrp};
+    HCU_CHECK(hcu_legendre_synthesis(ctx, g, cf, lmax, spin, nb, src, nullptr, lmax + 1, 1, full, phase));
     t0.stop();
     StageTimer t1(ctx, 2, &ctx->sht_ms[3]);
     HCU_CHECK(hcu_ring_fft_inverse(ctx, g, lmax, nb, phase, nullptr, 0, nrp, dst));
@@ -341,7 +343,30 @@ extern "C" int hcu_phase2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, in
   hcu_ptrs rows;
   for (int c = 0; c < HCU_MAX_BATCH; ++c)
     rows.p[c] = c < ncomp ? (double *)alm + 2 * (i64)c * alm_stride : nullptr;
-  return hcu_legendre_analysis(ctx, g, cf, lmax, spin, ncomp, phase, mlist, nm, rp_lo, rp_hi, fl, rows);
+  const i64 one[2] = {rp_lo, rp_hi};
+  return hcu_legendre_analysis(ctx, g, cf, lmax, spin, ncomp, phase, mlist, nm, 1, one, fl, rows);
+}
+
+extern "C" int hcu_phase2alm_blocks(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
+                                    const double *phase, const int32_t *mlist, int nm, int nblocks,
+                                    const int64_t *rp_bounds, const double *fl, void *alm,
+                                    int64_t alm_stride) {
+  HCU_ARG(rp_bounds && nblocks >= 1 && nblocks <= 16, "1 <= nblocks <= 16");
+  for (int b = 0; b < nblocks; ++b) HCU_ARG(rp_bounds[b] <= rp_bounds[b + 1], "rp_bounds must ascend");
+  HCU_CHECK(check_stage_args(ctx, nside, lmax, spin, ncomp, rp_bounds[0], rp_bounds[nblocks], mlist, nm));
+  HCU_ARG(phase && alm, "null pointer");
+  HCU_ARG(hcu_dev_accessible(phase) && hcu_dev_accessible(alm), "device pointers required");
+  HCU_ARG(!fl || hcu_dev_accessible(fl), "fl must be on the device");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  hcu_geom *g;
+  hcu_coef *cf;
+  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
+  HCU_CHECK(hcu_get_coef(ctx, lmax, spin, &cf));
+  hcu_ptrs rows;
+  for (int c = 0; c < HCU_MAX_BATCH; ++c)
+    rows.p[c] = c < ncomp ? (double *)alm + 2 * (i64)c * alm_stride : nullptr;
+  return hcu_legendre_analysis(ctx, g, cf, lmax, spin, ncomp, phase, mlist, nm, nblocks,
+                               (const i64 *)rp_bounds, fl, rows);
 }
 
 extern "C" int hcu_alm2phase(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
@@ -358,7 +383,28 @@ extern "C" int hcu_alm2phase(hcu_ctx *ctx, int64_t nside, int lmax, int spin, in
   hcu_ptrs rows;
   for (int c = 0; c < HCU_MAX_BATCH; ++c)
     rows.p[c] = c < ncomp ? (double *)alm + 2 * (i64)c * alm_stride : nullptr;
-  return hcu_legendre_synthesis(ctx, g, cf, lmax, spin, ncomp, rows, mlist, nm, rp_lo, rp_hi, phase);
+  const i64 one[2] = {rp_lo, rp_hi};
+  return hcu_legendre_synthesis(ctx, g, cf, lmax, spin, ncomp, rows, mlist, nm, 1, one, phase);
+}
+
+extern "C" int hcu_alm2phase_blocks(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
+                                    const void *alm, int64_t alm_stride, const int32_t *mlist, int nm,
+                                    int nblocks, const int64_t *rp_bounds, double *phase) {
+  HCU_ARG(rp_bounds && nblocks >= 1 && nblocks <= 16, "1 <= nblocks <= 16");
+  for (int b = 0; b < nblocks; ++b) HCU_ARG(rp_bounds[b] <= rp_bounds[b + 1], "rp_bounds must ascend");
+  HCU_CHECK(check_stage_args(ctx, nside, lmax, spin, ncomp, rp_bounds[0], rp_bounds[nblocks], mlist, nm));
+  HCU_ARG(phase && alm, "null pointer");
+  HCU_ARG(hcu_dev_accessible(phase) && hcu_dev_accessible(alm), "device pointers required");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  hcu_geom *g;
+  hcu_coef *cf;
+  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
+  HCU_CHECK(hcu_get_coef(ctx, lmax, spin, &cf));
+  hcu_ptrs rows;
+  for (int c = 0; c < HCU_MAX_BATCH; ++c)
+    rows.p[c] = c < ncomp ? (double *)alm + 2 * (i64)c * alm_stride : nullptr;
+  return hcu_legendre_synthesis(ctx, g, cf, lmax, spin, ncomp, rows, mlist, nm, nblocks,
+                                (const i64 *)rp_bounds, phase);
 }
 
 extern "C" int hcu_phase2map(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp, const double *phase,

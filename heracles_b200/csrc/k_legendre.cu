@@ -188,17 +188,23 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, int parity) {
 struct Setup {
   int g, mi, m, l0, pb, nrows, nchunk;
   i64 row0, cbase;
+  i64 nrp_b, rp_base, poff;  // ring pairs of this CTA's block, its first ring pair, its offset in phase
 };
 
 template <int SPIN>
 __device__ __forceinline__ bool setup_cta(const LegArgs &a, Setup &s, Rec<SPIN> &rec, int warp, int lane) {
-  const int ngroups = (int)((a.nrp_local + R - 1) / R);
+  const int ngroups = a.grp_start[a.nblk];
   s.g = blockIdx.x % ngroups;
   s.mi = blockIdx.x / ngroups;
+  int b = 0;
+  while (b + 1 < a.nblk && s.g >= a.grp_start[b + 1]) ++b;
+  s.nrp_b = a.blk_rp[b + 1] - a.blk_rp[b];
+  s.rp_base = a.blk_rp[b];
+  s.poff = (i64)a.nm * a.ncomp * 4 * (a.blk_rp[b] - a.blk_rp[0]);
   s.m = a.mlist ? a.mlist[s.mi] : s.mi;
   s.l0 = (SPIN == 0) ? s.m : (s.m > 2 ? s.m : 2);
-  s.row0 = (i64)s.g * R;
-  s.nrows = (int)min((i64)R, a.nrp_local - s.row0);
+  s.row0 = (i64)(s.g - a.grp_start[b]) * R;
+  s.nrows = (int)min((i64)R, s.nrp_b - s.row0);
   s.pb = (s.l0 + s.m) & 1;
   s.cbase = alm_index(a.lmax, 0, s.m);
   s.nchunk = (a.lmax - s.l0 + LC) / LC;
@@ -211,7 +217,7 @@ __device__ __forceinline__ bool setup_cta(const LegArgs &a, Setup &s, Rec<SPIN> 
   const int r = warp * 32 + lane;
   double sth = 1, chh = 1, shh = 1;
   if (r < s.nrows) {
-    const i64 rp = a.rp_lo + s.row0 + r;
+    const i64 rp = s.rp_base + s.row0 + r;
     rec.x = a.cth[rp];
     sth = a.sth[rp];
     chh = a.ch[rp];
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
   // ---- B fragments of this warp's 32 rings, both parities, resident in registers ----
   double bf[8][NJ][2][NBLK];
   {
-    const double *src = a.phase + ((i64)st.mi * a.nrp_local + st.row0) * a.ncomp * 4;
+    const double *src = a.phase + st.poff + ((i64)st.mi * st.nrp_b + st.row0) * a.ncomp * 4;
 #pragma unroll
     for (int k4 = 0; k4 < 8; ++k4) {
       const int r = warp * 32 + 4 * k4 + fa;
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(NT, 1) legendre_synthesis_kernel(LegArgs a) {
   Setup st;
   Rec<SPIN> rec;
   const bool active = setup_cta<SPIN>(a, st, rec, warp, lane);
-  double *dst = a.phase_out + ((i64)st.mi * a.nrp_local + st.row0) * a.ncomp * 4;
+  double *dst = a.phase_out + st.poff + ((i64)st.mi * st.nrp_b + st.row0) * a.ncomp * 4;
   if (!active) {  // every output row must be defined
     for (int i = threadIdx.x; i < st.nrows * a.ncomp * 4; i += NT) dst[i] = 0.0;
     return;
@@ -694,7 +700,7 @@ __global__ void coef_kernel(int lmax, int spin, double *tab, double *scale) {
 template <int SPIN, int NBLK>
 int launch_analysis(hcu_ctx *ctx, const LegArgs &a) {
   using K = ACfg<SPIN, NBLK>;
-  const i64 nblocks = (i64)((a.nrp_local + R - 1) / R) * a.nm;
+  const i64 nblocks = (i64)a.grp_start[a.nblk] * a.nm;
   if (nblocks <= 0) return HCU_OK;
   HCU_CUDA(cudaFuncSetAttribute(legendre_analysis_kernel<SPIN, NBLK>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
@@ -706,7 +712,7 @@ int launch_analysis(hcu_ctx *ctx, const LegArgs &a) {
 template <int SPIN, int NBLK>
 int launch_synthesis(hcu_ctx *ctx, const LegArgs &a) {
   using K = SCfg<SPIN, NBLK>;
-  const i64 nblocks = (i64)((a.nrp_local + R - 1) / R) * a.nm;
+  const i64 nblocks = (i64)a.grp_start[a.nblk] * a.nm;
   if (nblocks <= 0) return HCU_OK;
   HCU_CUDA(cudaFuncSetAttribute(legendre_synthesis_kernel<SPIN, NBLK>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
@@ -716,14 +722,19 @@ int launch_synthesis(hcu_ctx *ctx, const LegArgs &a) {
 }
 
 void fill_args(LegArgs &a, hcu_geom *g, hcu_coef *c, int lmax, int ncomp,
-               const int32_t *mlist_dev, int nm, i64 rp_lo, i64 rp_hi) {
+               const int32_t *mlist_dev, int nm, int nblk, const i64 *rp_bounds) {
   a.lmax = lmax;
   a.nm = nm;
   a.ncomp = ncomp;
   a.mlist = mlist_dev;
   a.phase = nullptr;
-  a.nrp_local = rp_hi - rp_lo;
-  a.rp_lo = rp_lo;
+  a.nblk = nblk;
+  a.grp_start[0] = 0;
+  for (int b = 0; b < nblk; ++b) {
+    a.blk_rp[b] = rp_bounds[b];
+    a.grp_start[b + 1] = a.grp_start[b] + (int)((rp_bounds[b + 1] - rp_bounds[b] + R - 1) / R);
+  }
+  a.blk_rp[nblk] = rp_bounds[nblk];
   a.cth = g->cth;
   a.sth = g->sth;
   a.ch = g->ch;
@@ -765,38 +776,40 @@ int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c) {
   return HCU_OK;
 }
 
-// alm[c][l, m] += sum over ring pairs [rp_lo, rp_hi) of lambda_lm(theta) x phase, for m in mlist
+// alm[c][l, m] += sum over the ring pairs of all blocks of lambda_lm(theta) x phase, for m in mlist
 int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
                           int spin, int ncomp, const double *phase,
-                          const int32_t *mlist_dev, int nm, i64 rp_lo, i64 rp_hi,
+                          const int32_t *mlist_dev, int nm, int nblk, const i64 *rp_bounds,
                           const double *fl_dev, const hcu_ptrs &alm) {
   HCU_ARG(ncomp >= 1 && ncomp <= hcu_legendre_batch(spin), "legendre batch size");
+  HCU_ARG(nblk >= 1 && nblk <= HCU_MAX_BLOCKS, "1 <= ring-pair blocks <= 16");
   LegArgs a;
-  fill_args(a, g, c, lmax, ncomp, mlist_dev, nm, rp_lo, rp_hi);
+  fill_args(a, g, c, lmax, ncomp, mlist_dev, nm, nblk, rp_bounds);
   a.phase = phase;
   a.fl = fl_dev;
   a.alm = alm;
   a.work = ctx->work_counters;
   // 8 output columns per n-block: 4 spin-0 maps, or 2 spin-2 fields (4 Q/U rows)
-  const int nblk = (ncomp + 3) / 4;
+  const int ncolblk = (ncomp + 3) / 4;
   if (spin == 0) {
-    switch (nblk) {
+    switch (ncolblk) {
       case 1: return launch_analysis<0, 1>(ctx, a);
       case 2: return launch_analysis<0, 2>(ctx, a);
       default: return launch_analysis<0, 3>(ctx, a);
     }
   }
-  return nblk == 1 ? launch_analysis<2, 1>(ctx, a) : launch_analysis<2, 2>(ctx, a);
+  return ncolblk == 1 ? launch_analysis<2, 1>(ctx, a) : launch_analysis<2, 2>(ctx, a);
 }
 
-// phase[(mi * nrp_local + rp - rp_lo) * ncomp + c] = (reN, imN, reS, imS) of sum_l a_lm lambda_lm(theta_rp)
+// phase (blocked layout, see LegArgs) = (reN, imN, reS, imS) of sum_l a_lm lambda_lm(theta_rp)
 int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
                            int spin, int ncomp, const hcu_ptrs &alm,
-                           const int32_t *mlist_dev, int nm, i64 rp_lo, i64 rp_hi,
+                           const int32_t *mlist_dev, int nm, int nblk, const i64 *rp_bounds,
                            double *phase) {
   HCU_ARG(ncomp >= 1 && ncomp <= hcu_legendre_batch(spin), "synthesis batch size");
+  HCU_ARG(nblk >= 1 && nblk <= HCU_MAX_BLOCKS, "1 <= ring-pair blocks <= 16");
   LegArgs a;
-  fill_args(a, g, c, lmax, ncomp, mlist_dev, nm, rp_lo, rp_hi);
+  fill_args(a, g, c, lmax, ncomp, mlist_dev, nm, nblk, rp_bounds);
   a.alm = alm;
   a.phase_out = phase;
   if (spin == 0) {

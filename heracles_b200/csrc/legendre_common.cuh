@@ -125,11 +125,17 @@ __device__ __forceinline__ bool ring_is_dead(int lmax, int m, int spin, double c
   return (double)m > res;
 }
 
+#define HCU_MAX_BLOCKS 16
 struct LegArgs {
   int lmax, nm, ncomp;      // ncomp: components present in `phase` rows (<= capacity of the template)
   const int *mlist;         // nullptr: m = index
-  const double *phase;      // [(mi * nrp_local + rpl) * ncomp + c] * 4
-  i64 nrp_local, rp_lo;
+  // ring pairs come in up to HCU_MAX_BLOCKS consecutive blocks [blk_rp[b], blk_rp[b+1]); phase is the
+  // concatenation over the blocks of [(mi * nrp_b + rp - blk_rp[b]) * ncomp + c] * 4 (one block: the
+  // plain [nm][nrp][ncomp][4] array).  grp_start[b] = first 256-ring-pair group of block b.
+  const double *phase;
+  int nblk;
+  int grp_start[HCU_MAX_BLOCKS + 1];
+  i64 blk_rp[HCU_MAX_BLOCKS + 1];
   const double *cth, *sth, *ch, *sh;  // indexed by global ring pair
   const double *coef;       // recursion coefficients, see hcu_build_coef
   const double *scale;      // s_l of the scaled recursion, lambda_l = s_l q_l

@@ -152,6 +152,31 @@ class StagedKernels:
             e1.record()
             self._events.append((e0, e1))
 
+    def phase2alm_blocks(self, phase, spin, nb, mlist, rp_bounds, alm):
+        """all source blocks of an exchanged phase array in one launch"""
+        import ctypes
+
+        if self.timing:
+            import torch
+
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        rb = (ctypes.c_int64 * len(rp_bounds))(*rp_bounds)
+        self._check(self.ctx.lib.hcu_phase2alm_blocks(self.ctx.handle, self.nside, self.lmax, spin, nb, phase.data_ptr(),
+                                                      self._p(mlist), mlist.numel(), len(rp_bounds) - 1, rb, None,
+                                                      alm.data_ptr(), alm.stride(0)))
+        if self.timing:
+            e1.record()
+            self._events.append((e0, e1))
+
+    def alm2phase_blocks(self, alm, spin, nb, mlist, rp_bounds, phase):
+        import ctypes
+
+        rb = (ctypes.c_int64 * len(rp_bounds))(*rp_bounds)
+        self._check(self.ctx.lib.hcu_alm2phase_blocks(self.ctx.handle, self.nside, self.lmax, spin, nb, alm.data_ptr(),
+                                                      alm.stride(0), self._p(mlist), mlist.numel(), len(rp_bounds) - 1, rb,
+                                                      phase.data_ptr()))
+
     def alm2phase(self, alm, spin, nb, mlist, rp_lo, rp_hi, phase):
         self._check(self.ctx.lib.hcu_alm2phase(self.ctx.handle, self.nside, self.lmax, spin, nb, alm.data_ptr(), alm.stride(0),
                                                self._p(mlist), mlist.numel(), rp_lo, rp_hi, phase.data_ptr()))
@@ -193,6 +218,39 @@ class DistributedTransform:
         self.mpos = torch.from_numpy(plan.mpos.copy()).to(dev)
         self._ws = {}
         self.exchanged_bytes = 0
+        self.timing = False   # CUDA events around the stages (device tensors only)
+        self._ev = {}
+
+    def _mark(self, name):
+        """context manager: accumulate device time of a stage under `name` when self.timing"""
+        import contextlib
+
+        if not self.timing:
+            return contextlib.nullcontext()
+        import torch
+
+        outer = self
+
+        class _T:
+            def __enter__(self):
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.b = torch.cuda.Event(enable_timing=True)
+                self.a.record()
+
+            def __exit__(self, *exc):
+                self.b.record()
+                outer._ev.setdefault(name, []).append((self.a, self.b))
+
+        return _T()
+
+    def stage_ms(self):
+        """device milliseconds per stage since the last call (synchronises)"""
+        import torch
+
+        torch.cuda.synchronize()
+        out = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in self._ev.items()}
+        self._ev = {}
+        return out
 
     # -- helpers ------------------------------------------------------------------------------
     def _buf(self, name, n):
@@ -224,17 +282,23 @@ class DistributedTransform:
         nrp_me, nm_me = hi - lo, len(plan.mlists[g])
         per = nb * 4
         send = self._buf("send", (plan.lmax + 1) * nrp_me * per)
-        self.k.map2phase(maps, lo, hi, self.m_all, send)
+        with self._mark("fft"):
+            self.k.map2phase(maps, lo, hi, self.m_all, send)
         in_splits = [len(plan.mlists[d]) * nrp_me * per for d in range(W)]
         out_splits = [nm_me * plan.nrp_of(s) * per for s in range(W)]
         recv = self._buf("recv", sum(out_splits))
-        self._all_to_all(recv, send, out_splits, in_splits)
+        with self._mark("a2a"):
+            self._all_to_all(recv, send, out_splits, in_splits)
         off = 0
-        for s in range(W):
-            slo, shi = plan.rp_range(s)
-            if nm_me and out_splits[s]:
-                self.k.phase2alm(recv[off:off + out_splits[s]], spin, nb, self.mlist_me, slo, shi, alm)
-            off += out_splits[s]
+        with self._mark("leg_ana"):
+            if nm_me and hasattr(self.k, "phase2alm_blocks") and W <= 16:
+                self.k.phase2alm_blocks(recv, spin, nb, self.mlist_me, list(plan.rp_bounds), alm)
+                return
+            for s in range(W):
+                slo, shi = plan.rp_range(s)
+                if nm_me and out_splits[s]:
+                    self.k.phase2alm(recv[off:off + out_splits[s]], spin, nb, self.mlist_me, slo, shi, alm)
+                off += out_splits[s]
 
     # -- one synthesis pass over a batch: maps (local rings) = S(alm) ------------------------------
     def _synthesis(self, alm, spin, maps):
@@ -247,15 +311,21 @@ class DistributedTransform:
         out_splits = [len(plan.mlists[s]) * nrp_me * per for s in range(W)]
         send = self._buf("send", sum(in_splits))
         off = 0
-        for d in range(W):
-            dlo, dhi = plan.rp_range(d)
-            if nm_me and in_splits[d]:
-                self.k.alm2phase(alm, spin, nb, self.mlist_me, dlo, dhi, send[off:off + in_splits[d]])
-            off += in_splits[d]
+        with self._mark("leg_syn"):
+            if nm_me and hasattr(self.k, "alm2phase_blocks") and W <= 16:
+                self.k.alm2phase_blocks(alm, spin, nb, self.mlist_me, list(plan.rp_bounds), send)
+            else:
+                for d in range(W):
+                    dlo, dhi = plan.rp_range(d)
+                    if nm_me and in_splits[d]:
+                        self.k.alm2phase(alm, spin, nb, self.mlist_me, dlo, dhi, send[off:off + in_splits[d]])
+                    off += in_splits[d]
         recv = self._buf("recv", sum(out_splits))
-        self._all_to_all(recv, send, out_splits, in_splits)
+        with self._mark("a2a"):
+            self._all_to_all(recv, send, out_splits, in_splits)
         # rows of recv are ordered by source rank = the order of plan.m_all
-        self.k.phase2map(recv, nb, self.mpos, lo, hi, maps)
+        with self._mark("ifft"):
+            self.k.phase2map(recv, nb, self.mpos, lo, hi, maps)
 
     # -- public -----------------------------------------------------------------------------------
     def map2alm(self, maps, spin: int, alm, fl=None):

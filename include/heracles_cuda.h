@@ -168,6 +168,17 @@ int hcu_phase2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
 int hcu_alm2phase(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
                   const void *alm, int64_t alm_stride, const int32_t *mlist, int nm,
                   int64_t rp_lo, int64_t rp_hi, double *phase);
+/* The same two Legendre stages over SEVERAL consecutive ring-pair blocks in ONE launch: block b
+ * covers [rp_bounds[b], rp_bounds[b+1]) and phase is the concatenation of the per-block arrays
+ * float64[nm][rp_bounds[b+1] - rp_bounds[b]][ncomp][4] -- exactly what an all-to-all of the
+ * per-rank blocks delivers (heracles_b200/dist.py).  nblocks <= 16. */
+int hcu_phase2alm_blocks(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
+                         const double *phase, const int32_t *mlist, int nm, int nblocks,
+                         const int64_t *rp_bounds, const double *fl, void *alm,
+                         int64_t alm_stride);
+int hcu_alm2phase_blocks(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
+                         const void *alm, int64_t alm_stride, const int32_t *mlist, int nm,
+                         int nblocks, const int64_t *rp_bounds, double *phase);
 int hcu_phase2map(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp, const double *phase,
                   const int32_t *mpos, int64_t rp_lo, int64_t rp_hi, double *maps,
                   int64_t map_stride);

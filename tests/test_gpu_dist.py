@@ -49,6 +49,14 @@ def test_staged_kernels_virtual_ranks(ctx, oracle, spin, W, nside, lmax):
             block = send[s][plan.m_off[g]:plan.m_off[g + 1]].contiguous()
             k.phase2alm(block, spin, nb, mlists[g], lo, hi, alm)
         alms.append(alm)
+    # the same analysis with all source blocks in ONE launch (hcu_phase2alm_blocks)
+    for g in range(W):
+        cat = torch.cat([send[s][plan.m_off[g]:plan.m_off[g + 1]].reshape(-1) for s in range(W)])
+        alm1 = torch.zeros(nb, plan.nalm, dtype=torch.complex128, device=dev)
+        k.phase2alm_blocks(cat, spin, nb, mlists[g], list(plan.rp_bounds), alm1)
+        torch.cuda.synchronize()
+        d = (alm1 - alms[g]).abs().max().item()
+        assert d <= 1e-13 * max(alms[g].abs().max().item(), 1e-300), d
     torch.cuda.synchronize()
     got = sum(a.cpu().numpy() for a in alms)
     ref = oracle.map2alm(nside, lmax, full, spin=spin)
@@ -68,6 +76,19 @@ def test_staged_kernels_virtual_ranks(ctx, oracle, spin, W, nside, lmax):
             k.alm2phase(alms[s], spin, nb, mlists[s], lo, hi, blk)
             recv[plan.m_off[s]:plan.m_off[s + 1]] = blk
         k.phase2map(recv, nb, mpos, lo, hi, out)
+    # hcu_alm2phase_blocks writes the blocks for all destinations at once
+    for s_ in range(W):
+        nm = len(plan.mlists[s_])
+        allblk = torch.full((nm * plan.nrp * nb * 4,), np.nan, dtype=torch.float64, device=dev)
+        k.alm2phase_blocks(alms[s_], spin, nb, mlists[s_], list(plan.rp_bounds), allblk)
+        off = 0
+        for d in range(W):
+            lo, hi = plan.rp_range(d)
+            one = torch.empty(nm, hi - lo, nb, 4, dtype=torch.float64, device=dev)
+            k.alm2phase(alms[s_], spin, nb, mlists[s_], lo, hi, one)
+            n = one.numel()
+            assert torch.equal(allblk[off:off + n], one.reshape(-1))
+            off += n
     torch.cuda.synchronize()
     back = out.cpu().numpy()
     assert not np.isnan(back).any()  # the blocks cover every pixel
