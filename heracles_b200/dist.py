@@ -38,10 +38,11 @@ __all__ = ["ShardPlan", "StagedKernels", "DistributedTransform", "reduce_maps", 
 class ShardPlan:
     """which ring pairs and which m every rank owns"""
 
-    def __init__(self, nside: int, lmax: int, world: int, cap_weight: float = 3.0):
+    def __init__(self, nside: int, lmax: int, world: int, cap_weight: float = 5.0):
         """cap_weight: cost of a polar-cap pixel relative to a belt pixel in the ring FFT stage (the
-        caps' Bluestein FFTs cost about three times cuFFT's power-of-two belt transforms per pixel);
-        the ring-pair blocks are balanced by this weighted pixel count."""
+        caps' Bluestein FFTs cost several times cuFFT's power-of-two belt transforms per pixel: fitted
+        from the per-rank stage times of an 8-GPU C4 run, profiles/); the ring-pair blocks are balanced
+        by this weighted pixel count."""
         if world < 1:
             raise ValueError("world must be >= 1")
         nrp = 2 * nside
