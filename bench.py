@@ -441,7 +441,7 @@ def cpu_sample(cfg, niter, threads=None):
     cores = oracle.num_threads()
     rng = np.random.default_rng(50)
     # 1. catalogue -> map at the real nside, 1 thread like the reference (healpy.py:157-160)
-    n = 1_000_000
+    n = 2_000_000
     lon = rng.uniform(0, 360, n)
     lat = np.degrees(np.arcsin(rng.uniform(-1, 1, n)))
     w = rng.uniform(0.5, 1.5, n)
@@ -462,7 +462,7 @@ def cpu_sample(cfg, niter, threads=None):
     rows_total = cfg["rows"] * cfg["nbins"]
     t_map = (t_pos + t_she) * rows_total
     # 2. transforms at reduced resolution, all threads, same niter; cost ~ nside * lmax^2 per map
-    ns = min(nside, 256)
+    ns = min(nside, 512)
     ls = 2 * ns
     m = rng.standard_normal((2, 12 * ns * ns))
     t = time.perf_counter()
