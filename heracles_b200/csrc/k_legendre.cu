@@ -158,6 +158,28 @@ __device__ __forceinline__ double2 fetch_coef(const LegArgs &a, i64 cbase, int l
   }
   return c2;
 }
+// asynchronous variant: global -> shared without a register hop (cp.async, zero fill past lmax);
+// completion is awaited with coef_wait() a sub-chunk later
+template <int SPIN>
+__device__ __forceinline__ void stage_coef_async(double *cf, const LegArgs &a, i64 cbase, int lsub, int lane) {
+  if (lane < SL) {
+    const int l = lsub + lane;
+    const int lc = min(l, max(a.lmax - 1, 0));
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(cf + 2 * lane);
+    if (SPIN == 0) {
+      const unsigned nbytes = (l < a.lmax) ? 8u : 0u;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(a.coef + cbase + lc), "r"(nbytes) : "memory");
+    } else {
+      const unsigned nbytes = (l < a.lmax) ? 16u : 0u;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst),
+                   "l"(reinterpret_cast<const double2 *>(a.coef) + cbase + lc), "r"(nbytes)
+                   : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void coef_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // the coefficients past lmax are zeroed here, a sub-chunk after the load was issued
 __device__ __forceinline__ void park_coef(double *cf, double2 c2, int lsub, int lmax, int lane) {
   if (lane < SL) {
@@ -317,7 +339,7 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
   // ---- prologue: sub-chunk 0 ----
   bool live_cur = false, live_nxt = false;
   park_coef(coefs, fetch_coef<SPIN>(a, cbase, st.l0, lane), st.l0, lmax, lane);
-  double2 cnext = fetch_coef<SPIN>(a, cbase, st.l0 + SL, lane);  // coefficients of sub-chunk 1
+  stage_coef_async<SPIN>(coefs + SL * 2, a, cbase, st.l0 + SL, lane);  // coefficients of sub-chunk 1
   __syncwarp();
   if (warp_alive) {
     live_cur = rec.sub_live();
@@ -389,12 +411,9 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
       // the recursion always runs one sub-chunk ahead (the one past the end is harmless: its
       // coefficients are zero and nothing reads it) so that the hot path below is branch free
       const bool prod = warp_alive;
-      __syncwarp();
-      if (prod) {
-        park_coef(coefs + ((sidx + 1) & 1) * (SL * 2), cnext, st.l0 + (sidx + 1) * SL, lmax, lane);
-        cnext = fetch_coef<SPIN>(a, cbase, st.l0 + (sidx + 2) * SL, lane);
-      }
-      __syncwarp();  // tile `sidx` and the coefficients of sub-chunk sidx + 1 are in place
+      coef_wait();
+      __syncwarp();  // coefficients of sub-chunk sidx + 1 have landed; everybody is done with those of sidx
+      if (prod) stage_coef_async<SPIN>(coefs + (sidx & 1) * (SL * 2), a, cbase, st.l0 + (sidx + 2) * SL, lane);  // tile `sidx` and the coefficients of sub-chunk sidx + 1 are in place
       if (prod) {
         live_nxt = rec.sub_live();
         rec.begin_sub();
@@ -542,7 +561,7 @@ __global__ void __launch_bounds__(NT, 1) legendre_synthesis_kernel(LegArgs a) {
   // ---- prologue: sub-chunk 0 and the a_lm of chunk 0 ----
   fetch_alm(st.l0);
   park_coef(coefs, fetch_coef<SPIN>(a, cbase, st.l0, lane), st.l0, lmax, lane);
-  double2 cnext = fetch_coef<SPIN>(a, cbase, st.l0 + SL, lane);  // coefficients of sub-chunk 1
+  stage_coef_async<SPIN>(coefs + SL * 2, a, cbase, st.l0 + SL, lane);  // coefficients of sub-chunk 1
   __syncwarp();
   if (warp_alive) {
     live_cur = rec.sub_live();
@@ -562,12 +581,9 @@ __global__ void __launch_bounds__(NT, 1) legendre_synthesis_kernel(LegArgs a) {
       double *tnxt = tiles + ((sidx + 1) & 1) * K::TILE;
       const double *ccur = coefs + ((sidx + 1) & 1) * (SL * 2);
       const bool prod = warp_alive;  // one sub-chunk ahead, also past the end (see the analysis kernel)
-      __syncwarp();
-      if (prod) {
-        park_coef(coefs + ((sidx + 1) & 1) * (SL * 2), cnext, st.l0 + (sidx + 1) * SL, lmax, lane);
-        cnext = fetch_coef<SPIN>(a, cbase, st.l0 + (sidx + 2) * SL, lane);
-      }
-      __syncwarp();  // tile `sidx`, btile and the coefficients of sub-chunk sidx + 1 are in place
+      coef_wait();
+      __syncwarp();  // coefficients of sub-chunk sidx + 1 have landed; everybody is done with those of sidx
+      if (prod) stage_coef_async<SPIN>(coefs + (sidx & 1) * (SL * 2), a, cbase, st.l0 + (sidx + 2) * SL, lane);  // tile `sidx`, btile and the coefficients of sub-chunk sidx + 1 are in place
       if (prod) {
         live_nxt = rec.sub_live();
         rec.begin_sub();
