@@ -629,7 +629,11 @@ def main():
     map_gbs = map_bytes * args.steps / max(stats["map_ms"], 1e-9) * 1e3 / 1e9
     roofline = {
         "kernel": "legendre_analysis_kernel", "bound": "fp64_fma", "achieved": leg_tflops, "peak": fp64_peak / 1e12,
-        "unit": "TFLOP/s", "frac": leg_tflops / (fp64_peak / 1e12), "traffic": None,
+        "unit": "TFLOP/s", "frac": leg_tflops / (fp64_peak / 1e12),
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from `ncu --set full` at the C4
+        # shape (nside 4096, lmax 8192, 4 spin-2 fields): 17.05 + 4.39 GB against 21.5 GB algorithmic
+        # (phase read once, alm read-modify-write); profiles/r01_ncu_full_legendre_analysis_spin2_c4shape.txt
+        "traffic": 21.43e9 if cfg_name == "C4" else None, "traffic_unit": "bytes per launch",
         "peak_source": "DFMA microkernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
         "share_of_step": stats["leg_ana_ms"] / total_ms,
     }
