@@ -89,6 +89,8 @@ extern "C" int hcu_trim(hcu_ctx *ctx) {
   free_buffer(&ctx->ws_alm);
   free_buffer(&ctx->ws_misc);
   free_buffer(&ctx->ws_state);
+  free_buffer(&ctx->ws_resid);
+  free_buffer(&ctx->ws_pw);
   return HCU_OK;
 }
 

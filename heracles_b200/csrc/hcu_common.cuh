@@ -111,7 +111,7 @@ struct hcu_ctx {
   int next_slot = 0;
   unsigned long long *bad_rows = nullptr; // device counter
   // workspaces
-  hcu_buffer ws_phase, ws_belt, ws_cap, ws_map, ws_alm, ws_misc, ws_state;
+  hcu_buffer ws_phase, ws_belt, ws_cap, ws_map, ws_alm, ws_misc, ws_state, ws_resid, ws_pw;
   // tables
   std::map<i64, hcu_geom> geom;
   std::map<std::pair<int, int>, hcu_coef> coef;

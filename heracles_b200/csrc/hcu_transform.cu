@@ -188,7 +188,9 @@ extern "C" int hcu_map2alm_many(hcu_ctx *ctx, int64_t nside, int lmax, int spin,
     HCU_CUDA(cudaMemsetAsync(dalm[c], 0, sizeof(double) * 2 * nalm, ctx->stream));
   }
   const double *dpw = pixel_weights;
-  hcu_buffer pwbuf, resid;
+  // residual and pixel-weight staging live in the context (cudaMalloc / cudaFree of tens of GB per call
+  // cost more than a second at nside 4096); hcu_trim releases them
+  hcu_buffer &pwbuf = ctx->ws_pw, &resid = ctx->ws_resid;
   if (pixel_weights && !hcu_dev_accessible(pixel_weights)) {
     HCU_CHECK(hcu_ws_reserve(ctx, &pwbuf, sizeof(double) * npix));
     HCU_CUDA(cudaMemcpyAsync(pwbuf.ptr, pixel_weights, sizeof(double) * npix, cudaMemcpyDefault, ctx->stream));
@@ -232,8 +234,6 @@ extern "C" int hcu_map2alm_many(hcu_ctx *ctx, int64_t nside, int lmax, int spin,
           cudaMemcpyAsync(alm[c], dalm[c], sizeof(double) * 2 * nalm, cudaMemcpyDefault, ctx->stream) != cudaSuccess)
         rc = HCU_ERR_CUDA;
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  if (pwbuf.ptr) cudaFree(pwbuf.ptr);
-  if (resid.ptr) cudaFree(resid.ptr);
   if (rc == HCU_OK && e != cudaSuccess) {
     hcu_set_error("hcu_map2alm: %s", cudaGetErrorString(e));
     rc = HCU_ERR_CUDA;
