@@ -118,12 +118,14 @@ extern "C" int hcu_destroy(hcu_ctx *ctx) {
     if (ctx->slot[i].host) cudaFreeHost(ctx->slot[i].host);
     if (ctx->slot[i].dev) cudaFree(ctx->slot[i].dev);
     if (ctx->slot[i].done) cudaEventDestroy(ctx->slot[i].done);
+    if (ctx->slot[i].ready) cudaEventDestroy(ctx->slot[i].ready);
   }
   cudaFree(ctx->bad_rows);
   cudaFree(ctx->work_counters);
   for (int i = 0; i < 6; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
   return HCU_OK;
 }
@@ -281,7 +283,9 @@ static int ensure_slots(hcu_ctx *ctx) {
     HCU_CUDA(cudaHostAlloc(&s.host, bytes, cudaHostAllocDefault));
     HCU_CUDA(cudaMalloc(&s.dev, bytes));
     HCU_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    HCU_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
   }
+  if (!ctx->copy_stream) HCU_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   return HCU_OK;
 }
 
@@ -314,12 +318,13 @@ static int stage_column(hcu_ctx *ctx, hcu_stage_slot &s, int col, const double *
     return HCU_OK;
   }
   double *d = s.dev + (i64)col * hcu_ctx::SLOT_ROWS;
+  // the copies run on their own stream so that they overlap the scatter kernel of the previous chunk
   if (kind == PK_PINNED) {
-    HCU_CUDA(cudaMemcpyAsync(d, src + r0, sizeof(double) * nr, cudaMemcpyHostToDevice, ctx->stream));
+    HCU_CUDA(cudaMemcpyAsync(d, src + r0, sizeof(double) * nr, cudaMemcpyHostToDevice, ctx->copy_stream));
   } else {
     double *h = s.host + (i64)col * hcu_ctx::SLOT_ROWS;
     parallel_memcpy(h, src + r0, sizeof(double) * nr);
-    HCU_CUDA(cudaMemcpyAsync(d, h, sizeof(double) * nr, cudaMemcpyHostToDevice, ctx->stream));
+    HCU_CUDA(cudaMemcpyAsync(d, h, sizeof(double) * nr, cudaMemcpyHostToDevice, ctx->copy_stream));
   }
   *dev = d;
   return HCU_OK;
@@ -341,7 +346,7 @@ static int map_values_impl(hcu_ctx *ctx, i64 nside, int scheme, const double *lo
     const i64 nr = std::min<i64>(hcu_ctx::SLOT_ROWS, n - r0);
     hcu_stage_slot &s = ctx->slot[ctx->next_slot];
     ctx->next_slot = (ctx->next_slot + 1) % hcu_ctx::NSLOT;
-    if (s.used) HCU_CUDA(cudaEventSynchronize(s.done));  // pinned buffer free again
+    if (s.used) HCU_CUDA(cudaEventSynchronize(s.done));  // slot (pinned + device buffer) free again
     const double *dlon, *dlat, *dval = nullptr;
     HCU_CHECK(stage_column(ctx, s, 0, lon, klon, r0, nr, &dlon));
     HCU_CHECK(stage_column(ctx, s, 1, lat, klat, r0, nr, &dlat));
@@ -358,6 +363,8 @@ static int map_values_impl(hcu_ctx *ctx, i64 nside, int scheme, const double *lo
         dvstride = hcu_ctx::SLOT_ROWS;
       }
     }
+    HCU_CUDA(cudaEventRecord(s.ready, ctx->copy_stream));
+    HCU_CUDA(cudaStreamWaitEvent(ctx->stream, s.ready, 0));
     HCU_CHECK(hcu_launch_map_values(ctx, nside, scheme, dlon, dlat, dval, dvstride, nv, nr,
                                     maps, mstride, flags, ipix_dev ? ipix_dev + r0 : nullptr));
     HCU_CUDA(cudaEventRecord(s.done, ctx->stream));

@@ -93,7 +93,8 @@ struct hcu_coef {
 struct hcu_stage_slot {
   double *host = nullptr; // pinned
   double *dev = nullptr;
-  cudaEvent_t done = nullptr;
+  cudaEvent_t done = nullptr;  // the kernel that consumed the slot has finished
+  cudaEvent_t ready = nullptr; // the H2D copies into the slot have landed
   bool used = false;
 };
 
@@ -101,11 +102,12 @@ struct hcu_ctx {
   int device = 0;
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr; // H2D staging of catalogue pages, overlapped with the scatter kernel
   cudaStream_t stream = nullptr;
   i64 n_launch = 0, n_cufft = 0;
   // staging for pageable host pages
   static const int NSLOT = 3;
-  static const i64 SLOT_ROWS = 1 << 18;
+  static const i64 SLOT_ROWS = 1 << 19;
   static const int SLOT_COLS = 4; // lon, lat, up to 2 value rows
   hcu_stage_slot slot[NSLOT];
   int next_slot = 0;
