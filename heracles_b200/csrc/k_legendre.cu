@@ -25,6 +25,9 @@
 //         synthesis  G[ring][col] += sum_l Lam[ring][l] (s_l a_lm)[l][col]; accumulators
 //                    stay in registers for the whole CTA, the a_lm chunk is prefetched a
 //                    chunk ahead into a warp-private shared tile; no CTA barrier at all.
+//   The recursion coefficients of the next sub-chunk arrive by cp.async (global -> shared without
+//   a register hop): a register-destination load that stays outstanding for a whole sub-chunk
+//   ties up a scoreboard the loop's shared-memory loads then wait on (measured: 15 %).
 // The recursion and the DMMAs are written into ONE instruction stream on purpose: a DFMA
 // chain in a warp of its own is starved by the scheduler as soon as two other warps of the
 // same SM sub-partition keep the FP64 pipe full of DMMAs (tools/mix_peak.cu: 17 000 clk per
