@@ -440,8 +440,14 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
             for (int p = 0; p < 2; ++p)
 #pragma unroll
               for (int nb = 0; nb < NBLK; ++nb)
+#ifndef HCU_EXP_NODMMA
                 dmma(acc[p][sb][nb][0], acc[p][sb][nb][1], af[j][p], bf[k4][j][p][nb]);
+#else
+                acc[p][sb][nb][0] += af[j][p] * 1e-300 + bf[k4][j][p][nb] * 1e-300;
+#endif
+#ifndef HCU_EXP_NOREC
           if (k4 & 1) rec.step4(tnxt, ccur, ring, pb, (k4 >> 1) * 4);
+#endif
         }
       } else if (prod) {
 #pragma unroll
@@ -450,6 +456,19 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
       if (prod) rec.end_sub();
       live_cur = prod ? live_nxt : false;
     }
+#ifdef HCU_EXP_NOFLUSH
+    {
+      double ssum = f_sc * f_fl;
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int sb = 0; sb < 2; ++sb)
+#pragma unroll
+          for (int nb = 0; nb < NBLK; ++nb) ssum += acc[p][sb][nb][0] + acc[p][sb][nb][1];
+      f_sc_prev += ssum;
+      continue;
+    }
+#endif
     // ---- first the deferred reduction of the previous chunk, then park this chunk's partial tile ----
     if (chk > 0) reduce_chunk(chk - 1, f_l_prev, f_sc_prev);
     f_l_prev = f_l;
@@ -471,7 +490,11 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
     __syncwarp();
     if (lane == 0) mbar_arrive(mbar + (chk & 1));
   }
+#ifdef HCU_EXP_NOFLUSH
+  if (f_sc_prev == 1.2345e-300) atomicAdd(a.alm.p[0], f_sc_prev);
+#else
   reduce_chunk(st.nchunk - 1, f_l_prev, f_sc_prev);
+#endif
   if (lane == 0 && a.work && n_rec > 0) {
     atomicAdd(a.work, n_rec * 32.0 * SL);
     atomicAdd(a.work + 1, n_acc * 32.0 * SL);
