@@ -628,7 +628,8 @@ def main():
     map_bytes = rows_step * (40 + (64 if cfg["she"] else 0))
     map_gbs = map_bytes * args.steps / max(stats["map_ms"], 1e-9) * 1e3 / 1e9
     roofline = {
-        "kernel": "legendre_analysis_kernel", "bound": "fp64_fma", "achieved": leg_tflops, "peak": fp64_peak / 1e12,
+        "kernel": "legendre_analysis_kernel", "bound": "tensor", "pipe": "FP64 (DMMA mma.sync.m8n8k4.f64 + DFMA share it)",
+        "achieved": leg_tflops, "peak": fp64_peak / 1e12,
         "unit": "TFLOP/s", "frac": leg_tflops / (fp64_peak / 1e12),
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from `ncu --set full` at the C4
         # shape (nside 4096, lmax 8192, 4 spin-2 fields): 17.05 + 4.39 GB against 21.5 GB algorithmic
