@@ -449,6 +449,7 @@ class DistributedPipeline:
 
     def put(self, spin: int, index: int, m) -> None:
         """copy partial map ``index`` of the given spin into the device stack"""
+        self.ctx.synchronize()  # whatever stream mapped into m has finished
         self.kernels.sync_streams()
         if hasattr(m, "to_device"):
             m.to_device()
