@@ -38,11 +38,12 @@ __all__ = ["ShardPlan", "StagedKernels", "DistributedTransform", "reduce_maps", 
 class ShardPlan:
     """which ring pairs and which m every rank owns"""
 
-    def __init__(self, nside: int, lmax: int, world: int, cap_weight: float = 5.0):
-        """cap_weight: cost of a polar-cap pixel relative to a belt pixel in the ring FFT stage (the
-        caps' Bluestein FFTs cost several times cuFFT's power-of-two belt transforms per pixel: fitted
-        from the per-rank stage times of an 8-GPU C4 run, profiles/); the ring-pair blocks are balanced
-        by this weighted pixel count."""
+    def __init__(self, nside: int, lmax: int, world: int, fft_cost=(3.08e-6, 0.0584, 3.39e-6)):
+        """fft_cost = (a, b, c): relative ring-FFT cost of a ring pair, a * M log2 M + b for a polar-cap
+        pair (M = power-of-two Bluestein length of its 4 sub-FFTs) and c * pixels for a belt pair (cuFFT).
+        Fitted (rms 3 %) to the per-rank FFT stage times of an 8-GPU C4 run (profiles/): small cap rings
+        are dominated by the per-ring term.  The ring-pair blocks are balanced by this cost;
+        fft_cost=None balances by pixel count."""
         if world < 1:
             raise ValueError("world must be >= 1")
         nrp = 2 * nside
@@ -54,8 +55,14 @@ class ShardPlan:
         self.nrp = nrp
         # pixels per ring pair: caps 2 x 4i, belt 2 x 4 nside, the equator ring counts once
         i = np.arange(1, nrp + 1, dtype=np.int64)
-        npair = np.where(i < nside, 8 * i * float(cap_weight), 8.0 * nside)
-        npair[-1] = 4 * nside
+        if fft_cost is None:
+            npair = np.where(i < nside, 8.0 * i, 8.0 * nside)
+            npair[-1] = 4 * nside
+        else:
+            a, b, c = fft_cost
+            m = 2.0 ** np.ceil(np.log2(np.maximum(2 * i - 1, 2)))
+            npair = np.where(i < nside, a * m * np.log2(m) + b, c * 8.0 * nside)
+            npair[-1] = c * 4.0 * nside
         cum = np.concatenate([[0], np.cumsum(npair)])
         bounds = [0]
         for g in range(1, world):

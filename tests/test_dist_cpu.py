@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_shard_plan(nside, lmax, world):
     from heracles_b200.dist import ShardPlan
 
-    plan = ShardPlan(nside, lmax, world, cap_weight=1.0)
+    plan = ShardPlan(nside, lmax, world, fft_cost=None)
     assert plan.rp_bounds[0] == 0 and plan.rp_bounds[-1] == 2 * nside
     assert all(b > a for a, b in zip(plan.rp_bounds, plan.rp_bounds[1:]))
     # pixel ranges of the blocks tile the map exactly once
@@ -26,7 +26,7 @@ def test_shard_plan(nside, lmax, world):
     # blocks are balanced by pixel count
     sizes = [sum(b - a for a, b in plan.pixel_ranges(g)) for g in range(world)]
     assert max(sizes) - min(sizes) <= 16 * nside + 8 * nside
-    # the default plan weights cap pixels (slower FFTs): polar blocks get fewer pixels, still a tiling
+    # the default plan balances the ring-FFT cost (cap rings are slower): polar blocks get fewer pixels, still a tiling
     wplan = ShardPlan(nside, lmax, world)
     wr = sorted(r for g in range(world) for r in wplan.pixel_ranges(g))
     assert wr[0][0] == 0 and wr[-1][1] == wplan.npix and all(a[1] == b[0] for a, b in zip(wr, wr[1:]))
