@@ -278,8 +278,10 @@ class Pipeline:
 
     def stage_cl(self):
         cfg = self.cfg
-        self.check(self.lib.hcu_alm2cl(self.h, self.ncomp, self.alm.data_ptr(), self.nalm, cfg["lmax"], self.ncomp,
-                                       self.alm.data_ptr(), self.nalm, cfg["lmax"], cfg["lmax"], self.cl.data_ptr()))
+        # at N > 1 the alm are m-distributed: every rank sums its own m (m = rank mod world) only
+        self.check(self.lib.hcu_alm2cl_mslice(self.h, self.ncomp, self.alm.data_ptr(), self.nalm, cfg["lmax"], self.ncomp,
+                                              self.alm.data_ptr(), self.nalm, cfg["lmax"], cfg["lmax"], self.world, self.rank,
+                                              self.cl.data_ptr()))
         if self.world > 1:  # partial sums over this rank's m
             import torch.distributed as dist
 

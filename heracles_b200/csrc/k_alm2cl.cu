@@ -19,6 +19,7 @@ struct ClArgs {
   const double2 *a, *b;
   i64 sa, sb;  // strides in complex elements
   int na, nb, lmax_a, lmax_b, lout, msplit;
+  int mstep, moff;  // only m = moff (mod mstep) contribute (m-distributed alm of the multi-GPU path)
   double *cl;
   bool same;  // a and b are the same array with the same stride: only j >= i is computed
 };
@@ -40,7 +41,8 @@ __global__ void __launch_bounds__(128) alm2cl_kernel(ClArgs p) {
   for (int i = 0; i < TA; ++i)
 #pragma unroll
     for (int j = 0; j < TB; ++j) acc[i][j] = 0.0;
-  for (int m = m0; m <= m1; ++m) {
+  const int mfirst = m0 + ((p.moff - m0) % p.mstep + p.mstep) % p.mstep;
+  for (int m = mfirst; m <= m1; m += p.mstep) {
     const i64 ia = (i64)m * (2 * p.lmax_a + 1 - m) / 2 + l;
     const i64 ib = (i64)m * (2 * p.lmax_b + 1 - m) / 2 + l;
     // the reference's m = 0 term is alm.real * alm2.real (twopoint.py:88): imaginary
@@ -78,11 +80,12 @@ __global__ void __launch_bounds__(128) alm2cl_kernel(ClArgs p) {
 
 }  // namespace
 
-extern "C" int hcu_alm2cl(hcu_ctx *ctx, int na, const void *a, int64_t stride_a,
-                          int lmax_a, int nb, const void *b, int64_t stride_b,
-                          int lmax_b, int lmax_out, double *cl) {
+static int alm2cl_impl(hcu_ctx *ctx, int na, const void *a, int64_t stride_a, int lmax_a, int nb,
+                       const void *b, int64_t stride_b, int lmax_b, int lmax_out, int mstep, int moff,
+                       double *cl) {
   HCU_ARG(ctx && a && b && cl, "hcu_alm2cl: null pointer");
   HCU_ARG(na >= 1 && nb >= 1 && lmax_a >= 0 && lmax_b >= 0 && lmax_out >= 0, "hcu_alm2cl: sizes");
+  HCU_ARG(mstep >= 1 && moff >= 0 && moff < mstep, "hcu_alm2cl: 0 <= m_offset < m_step");
   int lout = lmax_out;
   if (lmax_a < lout) lout = lmax_a;
   if (lmax_b < lout) lout = lmax_b;
@@ -97,6 +100,8 @@ extern "C" int hcu_alm2cl(hcu_ctx *ctx, int na, const void *a, int64_t stride_a,
   p.lmax_a = lmax_a;
   p.lmax_b = lmax_b;
   p.lout = lout;
+  p.mstep = mstep;
+  p.moff = moff;
   p.same = (a == b) && (stride_a == stride_b) && (na == nb) && (lmax_a == lmax_b);
   p.cl = cl;
   // enough m segments to fill the device a few times over
@@ -111,4 +116,17 @@ extern "C" int hcu_alm2cl(hcu_ctx *ctx, int na, const void *a, int64_t stride_a,
   alm2cl_kernel<<<grid, 128, 0, ctx->stream>>>(p);
   HCU_LAUNCH_CHECK(ctx);
   return HCU_OK;
+}
+
+extern "C" int hcu_alm2cl(hcu_ctx *ctx, int na, const void *a, int64_t stride_a,
+                          int lmax_a, int nb, const void *b, int64_t stride_b,
+                          int lmax_b, int lmax_out, double *cl) {
+  return alm2cl_impl(ctx, na, a, stride_a, lmax_a, nb, b, stride_b, lmax_b, lmax_out, 1, 0, cl);
+}
+
+// partial spectra from the m = m_offset (mod m_step) only: what a rank of the multi-GPU path owns
+extern "C" int hcu_alm2cl_mslice(hcu_ctx *ctx, int na, const void *a, int64_t stride_a,
+                                 int lmax_a, int nb, const void *b, int64_t stride_b,
+                                 int lmax_b, int lmax_out, int m_step, int m_offset, double *cl) {
+  return alm2cl_impl(ctx, na, a, stride_a, lmax_a, nb, b, stride_b, lmax_b, lmax_out, m_step, m_offset, cl);
 }

@@ -485,7 +485,9 @@ class DistributedPipeline:
         alm = torch.cat(parts) if len(parts) > 1 else parts[0]
         n, lmax = alm.shape[0], self.plan.lmax
         cl = torch.zeros(n, n, lmax + 1, dtype=torch.float64, device=self.device)
-        self.kernels._check(self.ctx.lib.hcu_alm2cl(self.ctx.handle, n, alm.data_ptr(), alm.stride(0), lmax, n, alm.data_ptr(),
-                                                    alm.stride(0), lmax, lmax, cl.data_ptr()))
+        # only the m this rank owns contribute (the other entries are zero and need not be read)
+        self.kernels._check(self.ctx.lib.hcu_alm2cl_mslice(self.ctx.handle, n, alm.data_ptr(), alm.stride(0), lmax, n,
+                                                           alm.data_ptr(), alm.stride(0), lmax, lmax, self.world, self.rank,
+                                                           cl.data_ptr()))
         allreduce_cl(cl, self.group)
         return cl

@@ -190,6 +190,11 @@ int hcu_phase2map(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp, const double
 int hcu_alm2cl(hcu_ctx *ctx, int na, const void *a, int64_t stride_a,
                int lmax_a, int nb, const void *b, int64_t stride_b, int lmax_b,
                int lmax_out, double *cl);
+/* the same sum restricted to m = m_offset (mod m_step): the partial spectra of one rank of the
+ * multi-GPU path, whose alm are m-distributed (summing them over the ranks gives hcu_alm2cl) */
+int hcu_alm2cl_mslice(hcu_ctx *ctx, int na, const void *a, int64_t stride_a,
+                      int lmax_a, int nb, const void *b, int64_t stride_b, int lmax_b,
+                      int lmax_out, int m_step, int m_offset, double *cl);
 
 /* ---- introspection --------------------------------------------------------- */
 /* device milliseconds of the stages of the last hcu_map2alm / hcu_alm2map call
