@@ -231,11 +231,12 @@ def test_pixel_weights(hb, oracle):
     assert relerr(alm, ref) < TOL
 
 
-def test_sparse_map_large_nside(hb, oracle):
-    # exact closed form at any nside: K non-zero pixels => a_lm = sum_k w v_k conj(Y_lm(theta_k, phi_k))
+@pytest.mark.parametrize("nside,lmax", [(1024, 2048), (4096, 8192)])
+def test_sparse_map_large_nside(hb, oracle, nside, lmax):
+    # exact closed form at any nside (here up to BASELINE's full size, C4): K non-zero pixels
+    # => a_lm = sum_k w v_k conj(Y_lm(theta_k, phi_k))
     from scipy.special import sph_harm_y
 
-    nside, lmax = 1024, 2048
     npix = 12 * nside**2
     rng = np.random.default_rng(8)
     ipix = np.array([0, 5, 1234567, npix // 2 + 3, npix - 1, 7 * nside * nside])
@@ -249,7 +250,8 @@ def test_sparse_map_large_nside(hb, oracle):
     mapper = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=0)
     alm = np.asarray(mapper.transform(m, spin=0))
     w = 4 * np.pi / npix
-    for l, mm in [(0, 0), (2, 1), (100, 37), (1500, 1499), (2048, 0), (2048, 2048), (2047, 1000), (777, 5)]:
+    for l, mm in [(0, 0), (2, 1), (100, 37), (1500, 1499), (lmax, 0), (lmax, lmax), (lmax - 1, lmax // 2 - 24), (777, 5),
+                  (lmax - 3, lmax - 200)]:
         if l <= 100:
             ylm = sph_harm_y(l, mm, theta, phi)
         else:  # scipy overflows at large l: use the oracle's long-double lambda_lm
@@ -260,3 +262,24 @@ def test_sparse_map_large_nside(hb, oracle):
         exp = w * np.sum(vals * np.conj(ylm))
         got = alm[mm * (2 * lmax + 1 - mm) // 2 + l]
         assert abs(got - exp) < 1e-9 * w * np.abs(vals).sum(), (l, mm, got, exp)
+
+
+def test_linearity_full_size_spin2(hb):
+    # size-independent property at BASELINE's full size (C4: nside 4096, lmax 8192), through the iterated
+    # transform (analysis + synthesis kernels, cap and belt FFTs): A(x + 2 y) = A(x) + 2 A(y)
+    nside, lmax = 4096, 8192
+    rng = np.random.default_rng(21)
+    mapper = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=1)
+    x = rng.standard_normal((2, 12 * nside**2))
+    y = rng.standard_normal((2, 12 * nside**2))
+    ax = np.asarray(mapper.transform(x, spin=2))
+    ay = np.asarray(mapper.transform(y, spin=2))
+    x += 2.0 * y
+    axy = np.asarray(mapper.transform(x, spin=2))
+    ref = ax + 2.0 * ay
+    for c in range(2):
+        assert relerr(axy[c], ref[c]) < 1e-12
+    # E and B of white noise carry comparable power and the l < 2 modes vanish
+    pe, pb = np.vdot(ax[0], ax[0]).real, np.vdot(ax[1], ax[1]).real
+    assert 0.8 < pe / pb < 1.25
+    assert np.all(ax[:, :2] == 0)
