@@ -642,7 +642,10 @@ def main():
     }
     roofline_map = {
         "kernel": "map_values_kernel", "bound": "hbm", "achieved": map_gbs, "peak": hbm_peak, "unit": "GB/s",
-        "frac": map_gbs / hbm_peak, "traffic": None,
+        "frac": map_gbs / hbm_peak,
+        # ncu --set full of one launch (1e6 rows): 113.7 MB of DRAM traffic for 40 MB algorithmic -- a random
+        # 8-byte atomic moves a whole 32-byte sector in and out (profiles/r01_ncu_full_map_values.txt)
+        "traffic": 113.7e6, "traffic_unit": "bytes per 1e6-row POS launch",
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
         "share_of_step": stats["map_ms"] / total_ms,
     }
