@@ -428,6 +428,11 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
         // DMMAs of sub-chunk sidx interleaved with the recursion of sub-chunk sidx + 1
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
+          // the four recursion groups go with k4 = 0, 2, 4, 6, so that the next tile is complete one k4 step
+          // before the hand-over and the tail of the DFMA chain hides behind the last DMMAs
+#ifndef HCU_EXP_NOREC
+          if (!(k4 & 1)) rec.step4(tnxt, ccur, ring, pb, (k4 >> 1) * 4);
+#endif
           const double *ta = tcur + ((k4 & 1) ? a_off1 : a_off0) + 32 * k4;
           double af[NJ][2];
 #pragma unroll
@@ -445,9 +450,7 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
 #else
                 acc[p][sb][nb][0] += af[j][p] * 1e-300 + bf[k4][j][p][nb] * 1e-300;
 #endif
-#ifndef HCU_EXP_NOREC
-          if (k4 & 1) rec.step4(tnxt, ccur, ring, pb, (k4 >> 1) * 4);
-#endif
+
         }
       } else if (prod) {
 #pragma unroll
