@@ -27,7 +27,6 @@ is computed.  Prints ONE JSON line (rank 0).
 from __future__ import annotations
 
 import argparse
-import ctypes
 import json
 import math
 import os

@@ -3,7 +3,6 @@ CPU tests of the drop-in boundary: the C-ABI library loads, exports every
 symbol include/heracles_cuda.h declares, and fails loudly without a device.
 No compute calls are made here.
 """
-import ctypes
 import os
 import re
 

@@ -5,7 +5,6 @@ for healpy.  Bit-exact pixel indices; maps equal to the sequential scatter up to
 the order of the floating-point adds (<= 1e-12 relative, exact when no pixel is
 hit twice).
 """
-import ctypes
 
 import numpy as np
 import numpy.testing as npt

@@ -2,7 +2,6 @@
 import argparse
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 import heracles_b200 as hb
 from heracles_b200 import _lib
