@@ -167,6 +167,11 @@ class Pipeline:
             self.plan = ShardPlan(nside, lmax, world)
             self.kernels = StagedKernels(self.ctx, nside, lmax)
             self.dist = DistributedTransform(self.kernels, self.plan, rank, niter=niter, device=torch.device("cuda"))
+            # a communicator of its own for the map all-reduce that overlaps the spin-0 transform (collectives
+            # of ONE communicator run in issue order, so the transform's all-to-all would queue behind it)
+            from heracles_b200.dist import _reduce_group
+
+            self.reduce_group = _reduce_group()
         self.make_catalogue()
 
     # synthetic catalogue: uniform positions, w ~ U(0.5,1.5), g ~ N(0,0.3)  
@@ -227,21 +232,24 @@ class Pipeline:
                 if self.cfg["she"]:
                     self.check(lib.hcu_map_values(h, nside, 0, lon0 + off, lat0 + off, wg0 + 2 * off, rows, 2, rows, she_ptr, npix, 0))
 
-    def stage_normalise(self):
+    def stage_normalise(self, scale=True, shift=True):
+        """scale: pos /= nbar, she /= wbar (linear: may precede the sum over ranks); shift: pos -= vis (once, after it)"""
         lib, h, npix = self.lib, self.h, self.npix
         for b in range(self.nbins):
             nbar, wbar = self.norm[b]
             p = self.maps[b].data_ptr()
-            self.check(lib.hcu_divide(h, p, npix, nbar))          # pos /= nbar
-            self.check(lib.hcu_add_scalar(h, p, npix, -1.0))      # pos -= vis (full sky)
-            if self.cfg["she"]:
-                self.check(lib.hcu_divide(h, self.maps[self.nbins + 2 * b].data_ptr(), 2 * npix, wbar))
+            if scale:
+                self.check(lib.hcu_divide(h, p, npix, nbar))          # pos /= nbar
+                if self.cfg["she"]:
+                    self.check(lib.hcu_divide(h, self.maps[self.nbins + 2 * b].data_ptr(), 2 * npix, wbar))
+            if shift:
+                self.check(lib.hcu_add_scalar(h, p, npix, -1.0))      # pos -= vis (full sky)
 
-    def stage_transform(self, stats):
+    def stage_transform(self, stats, spins=(0, 2)):
         lib, h, cfg = self.lib, self.h, self.cfg
         nb = self.nbins
-        calls = [(0, 0, nb)]
-        if cfg["she"]:
+        calls = [(0, 0, nb)] if 0 in spins else []
+        if cfg["she"] and 2 in spins:
             calls.append((2, nb, 2 * nb))
         if self.dist is not None:
             # every rank transforms its ring block / its m; alm rows are zero for foreign m
@@ -299,10 +307,23 @@ class Pipeline:
             self.stage_map()
             ev[1].record()
             if self.world > 1:
-                self.reduce_maps()
-            self.stage_normalise()
-            ev[2].record()
-            self.stage_transform(stats)
+                # sum the partial maps over the ranks: POS now, SHE asynchronously (NCCL's own stream) while
+                # the spin-0 transform runs; the linear normalisations come first, "- vis" after the sum
+                import torch.distributed as dist
+
+                self.stage_normalise(scale=True, shift=False)
+                dist.all_reduce(self.maps[:self.nbins])
+                work = dist.all_reduce(self.maps[self.nbins:], group=self.reduce_group, async_op=True) if self.cfg["she"] else None
+                self.stage_normalise(scale=False, shift=True)
+                ev[2].record()
+                self.stage_transform(stats, spins=(0,))
+                if work is not None:
+                    work.wait()
+                    self.stage_transform(stats, spins=(2,))
+            else:
+                self.stage_normalise()
+                ev[2].record()
+                self.stage_transform(stats)
             ev[3].record()
             self.stage_cl()
             ev[4].record()
@@ -312,12 +333,6 @@ class Pipeline:
         stats["sht_ms"] += ev[2].elapsed_time(ev[3])
         stats["cl_ms"] += ev[3].elapsed_time(ev[4])
         return ev[0].elapsed_time(ev[4])
-
-    def reduce_maps(self):
-        """partial maps of the ranks -> full maps (NCCL all-reduce on the pipeline's stream)"""
-        import torch.distributed as dist
-
-        dist.all_reduce(self.maps)
 
     # ---- end-to-end through the public API with pinned host pages ----
     def make_host_pool(self):

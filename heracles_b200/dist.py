@@ -419,6 +419,19 @@ def as_torch(arr, device):
     return torch.as_tensor(_CudaView(ptr, arr.shape, arr.dtype.str), device=device)
 
 
+_REDUCE_GROUP = None
+
+
+def _reduce_group():
+    """one extra world communicator per process, created on first use (creating one costs about a second)"""
+    global _REDUCE_GROUP
+    import torch.distributed as dist
+
+    if _REDUCE_GROUP is None:
+        _REDUCE_GROUP = dist.new_group()
+    return _REDUCE_GROUP
+
+
 class DistributedPipeline:
     """
     Maps of one ``CudaHealpixMapper`` (every rank mapped ITS pages into them) -> angular power
@@ -448,6 +461,9 @@ class DistributedPipeline:
         self.plan = ShardPlan(mapper.nside, mapper.lmax, self.world)
         self.kernels = StagedKernels(self.ctx, mapper.nside, mapper.lmax)
         self.transform = DistributedTransform(self.kernels, self.plan, self.rank, group=group, niter=mapper.niter, device=self.device)
+        # a second communicator for the spin-2 map reduction that overlaps the spin-0 transform
+        # (collectives of one communicator run in issue order)
+        self.reduce_group = _reduce_group() if self.world > 1 and group is None else group
         self.stacks = {}
         if npos:
             self.stacks[0] = torch.zeros(npos, self.plan.npix, dtype=torch.float64, device=self.device)
@@ -465,13 +481,14 @@ class DistributedPipeline:
         self.stacks[spin][index * n:(index + 1) * n].copy_(src)
         self.ctx.synchronize()  # the source may be freed by the caller
 
-    def alms(self, spin, finish=None):
-        """stack of one spin -> m-distributed alm tensor [rows, nalm]"""
+    def alms(self, spin, finish=None, reduced=False):
+        """stack of one spin -> m-distributed alm tensor [rows, nalm] (reduced: already summed over the ranks)"""
         import torch
 
         self.kernels.sync_streams()
         stack = self.stacks[spin]
-        reduce_maps(stack, self.group)
+        if not reduced:
+            reduce_maps(stack, self.group)
         if finish is not None:
             finish(stack, spin)
         alm = torch.zeros(stack.shape[0], self.plan.nalm, dtype=torch.complex128, device=self.device)
@@ -481,7 +498,19 @@ class DistributedPipeline:
     def spectra(self, finish=None):
         import torch
 
-        parts = [self.alms(spin, finish) for spin in (0, 2) if spin in self.stacks]
+        import torch.distributed as dist
+
+        parts, work = [], None
+        if 0 in self.stacks:
+            if 2 in self.stacks and self.world > 1:
+                # the spin-2 stack is summed over the ranks on NCCL's stream while the spin-0 maps are transformed
+                self.kernels.sync_streams()
+                work = dist.all_reduce(self.stacks[2], group=self.reduce_group, async_op=True)
+            parts.append(self.alms(0, finish))
+        if 2 in self.stacks:
+            if work is not None:
+                work.wait()
+            parts.append(self.alms(2, finish, reduced=work is not None))
         alm = torch.cat(parts) if len(parts) > 1 else parts[0]
         n, lmax = alm.shape[0], self.plan.lmax
         cl = torch.zeros(n, n, lmax + 1, dtype=torch.float64, device=self.device)
