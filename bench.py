@@ -266,7 +266,7 @@ class Pipeline:
             stats["leg_syn_ms"] += ms[2]
             # counters cover every analysis pass of the call; the recursion is shared by the
             # components of a batch (12 spin-0 maps / 4 spin-2 fields), so weight the batches
-            cap = 12 if spin == 0 else 8
+            cap = int(self.lib.hcu_legendre_batch_size(spin))
             nbat = -(-n // cap)
             for i in range(nbat):
                 nc = min(cap, n - i * cap)
@@ -276,7 +276,7 @@ class Pipeline:
         """executed flops per accumulated cell-batch of one analysis pass, summed over the Legendre batches"""
         nb, tot, nbat = self.nbins, 0.0, 0
         for spin, n in ((0, nb), (2, 2 * nb if self.cfg["she"] else 0)):
-            cap = 12 if spin == 0 else 8
+            cap = int(self.lib.hcu_legendre_batch_size(spin))
             for i in range(-(-n // cap) if n else 0):
                 nc = min(cap, n - i * cap)
                 tot += legendre_flops(spin, nc, 1.0, 1.0)
@@ -622,7 +622,7 @@ def main():
         rec, acc = (work1[0] - work0[0]) / nbat, (work1[1] - work0[1]) / nbat
         nb = cfg["nbins"]
         for spin, n in ((0, nb), (2, 2 * nb if cfg["she"] else 0)):
-            cap = 12 if spin == 0 else 8
+            cap = int(pipe.lib.hcu_legendre_batch_size(spin))
             for i in range(-(-n // cap) if n else 0):
                 stats["leg_ana_flops"] += legendre_flops(spin, min(cap, n - i * cap), rec, acc)
     if world > 1:

@@ -36,6 +36,8 @@
 // Work per (l, m, ring pair): recursion 2 (spin 0) / 4 (spin 2) FP64 ops shared by the
 // batch; accumulate 4 flop per spin-0 map, 16 per spin-2 field (SURVEY 8(d) counts the
 // recursion as 4 / 12 flop, which is what the reported flop numbers use).
+#include <stdlib.h>
+
 #include "legendre_common.cuh"
 
 namespace {
@@ -47,24 +49,6 @@ constexpr int LC = 32;       // l per chunk (flush / a_lm staging granularity)
 constexpr int NT = 32 * NW;
 constexpr int FLS = 34;      // column stride of a flush tile (32 l + 2: conflict free)
 
-__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-
-// Lam tile of one (j, parity): [ring 0..31][8 l], 16-byte units XOR-swizzled by the ring
-__device__ __forceinline__ int swzf(int ring) { return (((ring >> 1) & 1) << 1) | ((ring >> 2) & 1); }
-__device__ __forceinline__ int lam_off(int ring, int idx) {  // idx = l index within the parity, 0..7
-  return ring * 8 + 2 * ((idx >> 1) ^ swzf(ring)) + (idx & 1);
-}
-
-__device__ __forceinline__ double mask_d(double v, unsigned long long msk) {
-  return __longlong_as_double((long long)((unsigned long long)__double_as_longlong(v) & msk));
-}
-__device__ __forceinline__ double neg_d(double v) {  // sign flip on the integer pipe
-  return __longlong_as_double(__double_as_longlong(v) ^ (long long)0x8000000000000000ull);
-}
 
 template <int SPIN>
 struct Rec {
@@ -134,18 +118,6 @@ struct Rec {
   }
 };
 
-// prefetch loads: `asm volatile` pins them where they are written, a full sub-chunk (or chunk)
-// of tensor work ahead of their first use, instead of letting ptxas sink them next to it
-__device__ __forceinline__ double ldg_pin(const double *p) {
-  double r;
-  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ double2 ldg_pin2(const double2 *p) {
-  double2 r;
-  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
-  return r;
-}
 
 // lanes 0..15 fetch the recursion coefficients of the 16 steps starting at l = lsub
 template <int SPIN>
@@ -181,7 +153,6 @@ __device__ __forceinline__ void stage_coef_async(double *cf, const LegArgs &a, i
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void coef_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // the coefficients past lmax are zeroed here, a sub-chunk after the load was issued
 __device__ __forceinline__ void park_coef(double *cf, double2 c2, int lsub, int lmax, int lane) {
@@ -191,24 +162,6 @@ __device__ __forceinline__ void park_coef(double *cf, double2 c2, int lsub, int 
   }
 }
 
-// split-phase CTA barrier (arrive now, wait a chunk later) for the deferred alm flush
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, int parity) {
-  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-  unsigned done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  }
-}
 
 struct Setup {
   int g, mi, m, l0, pb, nrows, nchunk;
@@ -794,7 +747,31 @@ void fill_args(LegArgs &a, hcu_geom *g, hcu_coef *c, int lmax, int ncomp,
 
 }  // namespace
 
-int hcu_legendre_batch(int spin) { return spin == 0 ? 12 : 8; }
+// second-generation kernels (k_legendre2.cu)
+int hcu_legendre2_analysis(hcu_ctx *ctx, void *args, const i64 *rp_bounds, int spin, int ncomp, int nw);
+int hcu_legendre2_synthesis(hcu_ctx *ctx, void *args, const i64 *rp_bounds, int spin, int ncomp, int nw);
+
+// HCU_LEGENDRE_GEN=1 selects the first-generation kernels of this file (kept for A/B timing);
+// HCU_LEGENDRE_NW = 12 | 16 the warps per CTA of the second-generation analysis kernel
+static int legendre_gen() {
+  static int gen = -1;
+  if (gen < 0) {
+    const char *e = getenv("HCU_LEGENDRE_GEN");
+    gen = (e && e[0] == '1') ? 1 : 2;
+  }
+  return gen;
+}
+static int legendre_nw() {
+  static int nw = -1;
+  if (nw < 0) {
+    const char *e = getenv("HCU_LEGENDRE_NW");
+    nw = (e && atoi(e) == 12) ? 12 : 16;
+  }
+  return nw;
+}
+
+// components one Legendre launch takes: 8 spin-0 maps or 4 spin-2 fields (Q, U rows)
+int hcu_legendre_batch(int spin) { (void)spin; return 8; }
 
 int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c) {
   const i64 nalm = (i64)(c->lmax + 1) * (c->lmax + 2) / 2;
@@ -834,6 +811,7 @@ int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
   a.fl = fl_dev;
   a.alm = alm;
   a.work = ctx->work_counters;
+  if (legendre_gen() == 2) return hcu_legendre2_analysis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
   // 8 output columns per n-block: 4 spin-0 maps, or 2 spin-2 fields (4 Q/U rows)
   const int ncolblk = (ncomp + 3) / 4;
   if (spin == 0) {
@@ -857,6 +835,7 @@ int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
   fill_args(a, g, c, lmax, ncomp, mlist_dev, nm, nblk, rp_bounds);
   a.alm = alm;
   a.phase_out = phase;
+  if (legendre_gen() == 2) return hcu_legendre2_synthesis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
   if (spin == 0) {
     switch ((ncomp + 3) / 4) {
       case 1: return launch_synthesis<0, 1>(ctx, a);

@@ -125,6 +125,60 @@ __device__ __forceinline__ bool ring_is_dead(int lmax, int m, int spin, double c
   return (double)m > res;
 }
 
+// ---- helpers shared by k_legendre.cu and k_legendre2.cu ----
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Lam tile of one (j, parity): [ring 0..31][8 l], 16-byte units XOR-swizzled by the ring
+__device__ __forceinline__ int swzf(int ring) { return (((ring >> 1) & 1) << 1) | ((ring >> 2) & 1); }
+__device__ __forceinline__ int lam_off(int ring, int idx) {  // idx = l index within the parity, 0..7
+  return ring * 8 + 2 * ((idx >> 1) ^ swzf(ring)) + (idx & 1);
+}
+
+__device__ __forceinline__ double mask_d(double v, unsigned long long msk) {
+  return __longlong_as_double((long long)((unsigned long long)__double_as_longlong(v) & msk));
+}
+__device__ __forceinline__ double neg_d(double v) {  // sign flip on the integer pipe
+  return __longlong_as_double(__double_as_longlong(v) ^ (long long)0x8000000000000000ull);
+}
+
+// prefetch loads: `asm volatile` pins them where they are written, a full sub-chunk (or chunk)
+// of tensor work ahead of their first use, instead of letting ptxas sink them next to it
+__device__ __forceinline__ double ldg_pin(const double *p) {
+  double r;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ldg_pin2(const double2 *p) {
+  double2 r;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void coef_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// split-phase CTA barrier (arrive now, wait a chunk later) for the deferred alm flush
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, int parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+
 #define HCU_MAX_BLOCKS 16
 struct LegArgs {
   int lmax, nm, ncomp;      // ncomp: components present in `phase` rows (<= capacity of the template)

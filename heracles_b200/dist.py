@@ -27,6 +27,8 @@ stand-in that evaluates the stages with the oracle.
 
 from __future__ import annotations
 
+import hashlib
+
 import numpy as np
 
 __all__ = ["ShardPlan", "StagedKernels", "DistributedTransform", "reduce_maps", "allreduce_cl", "as_torch", "DistributedPipeline"]
@@ -371,10 +373,12 @@ class DistributedTransform:
         import torch
 
         lmax = self.plan.lmax
-        key = ("fl", id(fl))
+        # keyed by CONTENT: callers pass temporaries (mapper._fl(spin)), whose id() is recycled
+        # as soon as the previous filter is freed -- the spin-0 window must never serve spin 2
+        fl = np.ascontiguousarray(fl, dtype=np.float64)
+        key = ("fl", hashlib.sha1(fl.tobytes()).hexdigest())
         t = self._ws.get(key)
         if t is None:
-            fl = np.asarray(fl, dtype=np.float64)
             full = np.concatenate([fl[m:lmax + 1] for m in range(lmax + 1)])
             t = torch.from_numpy(full).to(self.device).to(torch.complex128)
             self._ws[key] = t

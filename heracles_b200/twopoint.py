@@ -140,17 +140,19 @@ def angular_power_spectra(
     staged: dict = {}
 
     def dev(a):
+        # the entry keeps `a` itself alive: a lazily loading alm mapping hands out a NEW array per
+        # access, and a freed array's id() would otherwise be recycled for a different (k, i)
         key = id(a)
         if key not in staged:
             if isinstance(a, DeviceArray) and a.device_ptr is not None:
-                staged[key] = a
+                staged[key] = (a, a)
             else:  # host alm: upload once, reuse for every pair it takes part in
                 h = np.ascontiguousarray(a, dtype=np.complex128)
                 d = DeviceArray.zeros(ctx, h.shape, dtype=np.complex128)
                 ctx.memcpy(d.device_ptr, h.__array_interface__["data"][0], h.nbytes)
                 ctx.synchronize()
-                staged[key] = d
-        return staged[key]
+                staged[key] = (a, d)
+        return staged[key][1]
 
     for (k1, i1), (k2, i2) in pairs:
         if (k1, k2, i1, i2) in cls or (k2, k1, i2, i1) in cls:

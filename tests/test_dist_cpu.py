@@ -184,3 +184,32 @@ def test_distributed_transform_gloo(spin, niter, world):
     assert err < 1e-12, err
     assert cerr < 1e-12, cerr
     assert nbytes > 0
+
+
+def test_deconvolution_filter_cache_is_keyed_by_content():
+    """DistributedPipeline passes a fresh temporary per spin; a cache keyed on id() served the
+    spin-0 pixel window to the spin-2 alm once the first temporary was freed and its id recycled"""
+    from heracles_b200.dist import DistributedTransform, ShardPlan
+
+    lmax = 6
+    dt = DistributedTransform(None, ShardPlan(4, lmax, 1), 0, niter=0)
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    for rep in range(8):  # allocate / free the same-sized temporary repeatedly: ids do get reused
+        for val in (2.0, 3.0):
+            fl = np.full(lmax + 1, val)
+            full = dt._fl_full(fl)
+            assert full.shape == (nalm,)
+            assert float(full.real.min()) == val == float(full.real.max())
+            del fl
+    assert len([k for k in dt._ws if isinstance(k, tuple)]) == 2
+
+
+def test_angular_power_spectra_staging_keeps_lazy_alms_alive():
+    """the upload cache of angular_power_spectra must not be fooled by recycled ids of
+    lazily loaded alm (a mapping that returns a NEW array per access, as heracles' AlmFits does)"""
+    import inspect
+
+    from heracles_b200 import twopoint
+
+    src = inspect.getsource(twopoint.angular_power_spectra)
+    assert "staged[key] = (a, d)" in src and "staged[key] = (a, a)" in src

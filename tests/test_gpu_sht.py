@@ -283,3 +283,37 @@ def test_linearity_full_size_spin2(hb):
     pe, pb = np.vdot(ax[0], ax[0]).real, np.vdot(ax[1], ax[1]).real
     assert 0.8 < pe / pb < 1.25
     assert np.all(ax[:, :2] == 0)
+
+
+@pytest.mark.parametrize("name", ["sht_c2.npz", "sht_c3.npz"])
+def test_full_map_parity_baseline_configs(hb, name):
+    """full random maps at BASELINE.json's C2 / C3 sizes against the oracle's digest
+    (tests/golden/make_sht_golden.py: sampled alm over the whole triangle, row norms, full auto spectra)"""
+    import os
+
+    from conftest import GOLDEN
+
+    if not os.path.exists(os.path.join(GOLDEN, name)):
+        pytest.skip(f"{name} not generated")
+    g = golden(name)
+    nside, lmax, n0, n2, seed = (int(g[k]) for k in ("nside", "lmax", "n0", "n2", "seed"))
+    idx = g["index"]
+    rng0 = np.random.default_rng(seed)
+    m0 = rng0.standard_normal((n0, 12 * nside * nside))
+    m2 = np.random.default_rng(seed + 7).standard_normal((2 * n2, 12 * nside * nside))
+    for niter in g["niters"]:
+        mapper = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=int(niter))
+        a0 = np.asarray(mapper.transform(m0, spin=0))
+        a2 = np.asarray(mapper.transform(m2.reshape(n2, 2, -1), spin=2)).reshape(2 * n2, -1)
+        for spin, a in ((0, a0), (2, a2)):
+            ref_s, ref_n, ref_cl = (g[f"s{spin}_n{niter}_{k}"] for k in ("samples", "norm", "cl"))
+            for c in range(a.shape[0]):
+                rms = ref_n[c] / np.sqrt(a.shape[1])
+                err = np.abs(a[c, idx] - ref_s[c]).max() / rms
+                assert err < 10 * TOL, (name, spin, int(niter), c, err)
+                nrm = np.sqrt((np.abs(a[c]) ** 2).sum())
+                assert abs(nrm - ref_n[c]) < TOL * ref_n[c], (name, spin, int(niter), c)
+                cl = hb.alm2cl(a[c])
+                lmin = spin
+                rel = np.abs(cl[lmin:] - ref_cl[c][lmin:]).max() / np.abs(ref_cl[c][lmin:]).max()
+                assert rel < TOL, (name, spin, int(niter), c, rel)

@@ -26,7 +26,9 @@ for r in range(a.reps):
     _lib.check(ctx.lib.hcu_map2alm(ctx.handle, a.nside, lmax, a.spin, a.nmaps, maps.data_ptr(), npix, None, None, a.niter, None, alm.data_ptr(), nalm))
     ms = ctx.sht_timing()
     rec, acc = ctx.sht_work()
-    nb = min(a.nmaps, 12 if a.spin == 0 else 8)
+    nb = min(a.nmaps, int(ctx.lib.hcu_legendre_batch_size(a.spin)))
     fl = rec * 4 + acc * 4 * nb if a.spin == 0 else rec * 12 + acc * 16 * (nb // 2)
+    npass = 1 + a.niter
+    syn = f"syn {fl / npass * a.niter / ms[2] / 1e9:.2f} TF/s  " if a.niter else ""
     print(f"rep {r}: fft {ms[0]:.2f} ms  leg_ana {ms[1]:.2f} ms  leg_syn {ms[2]:.2f}  ifft {ms[3]:.2f}  "
-          f"ana {fl / ms[1] / 1e9:.2f} TF/s of {peak / 1e12:.1f}  rec {rec:.3g} acc {acc:.3g} live {acc / max(rec, 1):.2f}")
+          f"ana {fl / ms[1] / 1e9:.2f} TF/s of {peak / 1e12:.1f}  {syn}rec {rec:.3g} acc {acc:.3g} live {acc / max(rec, 1):.2f}")
