@@ -52,6 +52,10 @@ CONFIGS = {
     "C4": dict(nside=4096, lmax=8192, nbins=10, rows=200_000_000, she=True,
                text="nside=4096 lmax=8192 10 tomographic bins x POS+SHE from 2e9 synthetic galaxies"),
 }
+C5 = dict(nside=8192, lmax=16384, fields=40,
+          text="nside=8192 lmax=16384 spin-2 shear map2alm batch of 40 (Q,U) maps (SHT-only stress)")
+# small configuration on which bench.py checks the N-GPU result against a 1-GPU run before timing
+PARITY_CFG = dict(nside=256, lmax=512, nbins=2, rows=2_000_000, she=True, text="multi-GPU parity check")
 PAGE_ROWS = 1_000_000  # heracles/catalog/base.py:315
 POOL_PAGES = 64        # distinct pages per bin, cycled to reach the row count
 METRIC = "catalog_to_cl_seconds_per_run"
@@ -118,6 +122,24 @@ class ClockSampler:
         }
 
 
+def checksum_matrix(cl):
+    """ONE checksum for every arm and every N: the sum over l of all component spectra C_l^{ij} with i <= j
+    (cl: [ncomp, ncomp, lmax + 1] host array; the lower triangle is ignored)"""
+    return float(np.triu(cl.sum(axis=-1)).sum())
+
+
+def checksum_results(cls):
+    """the same number from the dictionary angular_power_spectra returns: every block holds distinct component
+    pairs except the (BE) element of a spin-2 auto block, which repeats (EB)"""
+    tot = 0.0
+    for (k1, k2, i1, i2), c in cls.items():
+        c = np.asarray(c)
+        tot += float(c.sum())
+        if c.ndim == 3 and k1 == k2 and i1 == i2:
+            tot -= float(c[1, 0].sum())
+    return tot
+
+
 def pick_config(name, free_bytes):
     if name != "auto":
         return name
@@ -147,6 +169,7 @@ class Pipeline:
         self.cfg, self.niter, self.rank, self.world = cfg, niter, rank, world
         self.torch, self.hb = torch, hb
         self.ctx = hb.get_context(torch.cuda.current_device())
+        self.ctx.set_timing(True)  # stage_ms_per_step / roofline need the per-stage CUDA events
         self.lib = self.ctx.lib
         self.h = self.ctx.handle
         self.stream = torch.cuda.Stream()
@@ -426,7 +449,7 @@ class Pipeline:
             cl = dp.spectra(finish=finish)
             host = cl.cpu().numpy()
             d2h = host.nbytes
-            checksum = float(np.triu(host.sum(axis=-1)).sum())
+            checksum = checksum_matrix(host)
             ncl = self.ncomp * (self.ncomp + 1) // 2
             dt = time.perf_counter() - t0
             if self.rank == 0 and os.environ.get("HCU_BENCH_VERBOSE"):
@@ -437,27 +460,35 @@ class Pipeline:
             hb.update_metadata(a, spin=0 if k == "POS" else 2)
         cls = hb.angular_power_spectra(alms, debias=False)
         d2h = sum(np.asarray(c).nbytes for c in cls.values())
-        checksum = float(sum(np.asarray(c).sum() for c in cls.values()))
+        checksum = checksum_results(cls)
         dt = time.perf_counter() - t0
         if os.environ.get("HCU_BENCH_VERBOSE"):
             print(f"e2e: mapping {t_map:.3f} s, transform + Cl {dt - t_map:.3f} s", file=sys.stderr, flush=True)
         return dt, h2d, d2h, checksum, len(cls)
 
 
-def cpu_sample(cfg, niter, threads=None):
+def host_threads():
+    """the cores this process may use -- NOT OMP_NUM_THREADS, which torchrun sets to 1"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
+def cpu_sample(cfg, niter, threads=None, sample_nside=512, sample_rows=2_000_000):
     """
-    Time the oracle (CPU restatement of the reference path) on a bounded sample
-    of the configuration and scale to one full run.  Returns (seconds_per_run, info).
+    Time the oracle (CPU restatement of the reference path) on a BOUNDED sample of the configuration and scale
+    to one full run with the stages' cost laws (rows; nside * lmax^2 per map and pass; nalm per spectrum).
+    Returns (seconds_per_run, info).  The number is an extrapolation and says so (info["extrapolated"]).
     """
     import oracle
 
     oracle.build()
-    if threads:
-        oracle.set_num_threads(threads)
+    oracle.set_num_threads(threads or host_threads())
     cores = oracle.num_threads()
     rng = np.random.default_rng(50)
     # 1. catalogue -> map at the real nside, 1 thread like the reference (healpy.py:157-160)
-    n = 2_000_000
+    n = sample_rows
     lon = rng.uniform(0, 360, n)
     lat = np.degrees(np.arcsin(rng.uniform(-1, 1, n)))
     w = rng.uniform(0.5, 1.5, n)
@@ -478,7 +509,7 @@ def cpu_sample(cfg, niter, threads=None):
     rows_total = cfg["rows"] * cfg["nbins"]
     t_map = (t_pos + t_she) * rows_total
     # 2. transforms at reduced resolution, all threads, same niter; cost ~ nside * lmax^2 per map
-    ns = min(nside, 512)
+    ns = min(nside, sample_nside)
     ls = 2 * ns
     m = rng.standard_normal((2, 12 * ns * ns))
     t = time.perf_counter()
@@ -503,24 +534,98 @@ def cpu_sample(cfg, niter, threads=None):
     total = t_map + t_sht + t_cl
     info = {
         "value": total, "unit": UNIT, "cores": cores, "kind": "port",
+        "extrapolated": ns != nside or n != rows_total,
+        "scaling_law": "map: rows; map2alm: nside * lmax^2 per map and pass; alm2cl: nalm per spectrum",
+        "sampled": {"rows": n, "nside": ns, "lmax": ls, "niter": niter},
+        "stage_seconds_extrapolated": {"map": t_map, "sht": t_sht, "cl": t_cl},
         "sample": (f"oracle (CPU restatement of the healpy/ducc path): ang2pix+scatter on {n} rows at nside={nside} "
                    f"(1 thread, {t_pos * 1e9:.0f}+{t_she * 1e9:.0f} ns/row) x {rows_total:.3g} rows; map2alm spin0+spin2 "
                    f"niter={niter} at nside={ns} lmax={ls} ({cores} threads) scaled by nside*lmax^2 x {cfg['nbins']} bins; "
-                   f"alm2cl at lmax={ls} scaled by nalm x {ncomp * (ncomp + 1) // 2} spectra; "
-                   f"extrapolated stage seconds map/sht/cl = {t_map:.1f}/{t_sht:.1f}/{t_cl:.1f}"),
+                   f"alm2cl at lmax={ls} scaled by nalm x {ncomp * (ncomp + 1) // 2} spectra"),
     }
     return total, info
 
 
+def cpu_full(cfg, niter, threads=None):
+    """
+    The WHOLE configuration on the host cores, nothing extrapolated (affordable for C1 and C2 only): every page
+    of every bin through the oracle's ang2pix + scatter (1 thread, like the reference), the Field normalisation,
+    map2alm of every map (all threads) and every component spectrum.  Returns (seconds, info).
+    """
+    import oracle
+
+    oracle.build()
+    oracle.set_num_threads(threads or host_threads())
+    cores = oracle.num_threads()
+    nside, lmax, nb = cfg["nside"], cfg["lmax"], cfg["nbins"]
+    npix = 12 * nside * nside
+    pages = max(1, cfg["rows"] // PAGE_ROWS)
+    rows = min(PAGE_ROWS, cfg["rows"])
+    t_start = time.perf_counter()
+    pos = np.zeros((nb, npix))
+    she = np.zeros((nb, 2, npix)) if cfg["she"] else None
+    t_gen = 0.0
+    for b in range(nb):
+        wsum = 0.0
+        for p in range(pages):
+            tg = time.perf_counter()
+            rng = np.random.default_rng(50 + 1000 * b + p)
+            lon = rng.uniform(0, 360, rows)
+            lat = np.degrees(np.arcsin(rng.uniform(-1, 1, rows)))
+            w = rng.uniform(0.5, 1.5, rows)
+            g = rng.normal(0, 0.3, (2, rows)) * w if cfg["she"] else None
+            t_gen += time.perf_counter() - tg  # synthetic page generation is not part of the path
+            oracle.map_values(nside, lon, lat, pos[b], w)
+            if she is not None:
+                oracle.map_values(nside, lon, lat, she[b], g)
+            wsum += w.sum()
+        ngal = pages * rows
+        wmean = wsum / ngal
+        pos[b] /= ngal * wmean / npix
+        pos[b] -= 1.0
+        if she is not None:
+            she[b] /= ngal / (4 * math.pi) * wmean * (4 * math.pi / npix)
+    t_map = time.perf_counter() - t_start - t_gen
+    t = time.perf_counter()
+    alm = [oracle.map2alm(nside, lmax, pos, spin=0, niter=niter)]
+    if she is not None:
+        alm.append(oracle.map2alm(nside, lmax, she.reshape(2 * nb, npix), spin=2, niter=niter))
+    alm = np.concatenate(alm)
+    t_sht = time.perf_counter() - t
+    t = time.perf_counter()
+    ncomp = alm.shape[0]
+    cl = np.zeros((ncomp, ncomp, lmax + 1))
+    for i in range(ncomp):
+        for j in range(i, ncomp):
+            cl[i, j] = oracle.alm2cl(alm[i], alm[j])
+    t_cl = time.perf_counter() - t
+    total = t_map + t_sht + t_cl
+    info = {"value": total, "unit": UNIT, "cores": cores, "kind": "port", "extrapolated": False,
+            "stage_seconds": {"map": t_map, "sht": t_sht, "cl": t_cl}, "checksum": checksum_matrix(cl),
+            "sample": f"the whole configuration ({cfg['rows'] * nb:.3g} rows, {ncomp} components, niter={niter}), measured"}
+    return total, info
+
+
 def run_reference(args, cfg_name):
+    """`--impl reference`: the CPU arm.  healpy/ducc cannot be installed here, so this is the
+    oracle port on all host cores.  Rank 0 only; the other ranks exit without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = CONFIGS[cfg_name]
-    times = []
-    info = None
+    threads = host_threads()
+    times, info = [], None
+    full = args.cpu_full and cfg_name in ("C1", "C2")
     for i in range(args.warmup + args.steps):
-        t, info = cpu_sample(cfg, args.niter)
+        if full:
+            if i < args.warmup:
+                continue  # a full CPU pass needs no warm-up repeats (minutes each)
+            t, info = cpu_full(cfg, args.niter, threads)
+        else:
+            # warm-up steps on a cheap sample (page cache, thread pool, tables), timed steps on the real one
+            warm = i < args.warmup
+            t, info = cpu_sample(cfg, args.niter, threads, sample_nside=128 if warm else 512,
+                                 sample_rows=200_000 if warm else 2_000_000)
         if i >= args.warmup:
             times.append(t)
     val = float(np.mean(times))
@@ -529,12 +634,165 @@ def run_reference(args, cfg_name):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{cfg_name}: {cfg['text']}", "niter": args.niter,
-                   "note": "healpy/ducc are not installable here: the CPU arm is the oracle port, bounded sample scaled to the full run"},
+        "config": bench_config(cfg_name, cfg, args.niter),
+        "note": "healpy/ducc are not installable here: the CPU arm is the oracle port (kind 'port') on all host cores",
         "cpu_baseline": info,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def bench_config(cfg_name, cfg, niter):
+    """the `config` object both arms print (same keys, so the driver can match them)"""
+    ncomp = cfg["nbins"] * (3 if cfg["she"] else 1)
+    pages = max(1, cfg["rows"] // PAGE_ROWS)
+    return {
+        "workload": f"{cfg_name}: {cfg['text']}", "nside": cfg["nside"], "lmax": cfg["lmax"],
+        "fields": cfg["nbins"] * (2 if cfg["she"] else 1), "rows": cfg["rows"] * cfg["nbins"], "niter": niter,
+        "spectra": ncomp * (ncomp + 1) // 2,
+        "pages": f"{pages} pages of {min(PAGE_ROWS, cfg['rows'])} rows per bin cycling a pool of {min(POOL_PAGES, pages)} distinct pages",
+        "l2": "inputs larger than L2 (catalogue and maps are GBs); no flush needed",
+    }
+
+
+def dist_parity_check(args, rank, world, torch, hb):
+    """
+    N > 1: before anything is timed, the ring-block / m-distributed pipeline over all ranks is compared with the
+    single-GPU pipeline (run redundantly on every rank) on a small configuration.  Returns the largest
+    |dC_l^{ij}| / sqrt(C_l^{ii} C_l^{jj}) over all component pairs and l; bench.py refuses to time a run whose
+    ranks disagree with one GPU by more than 1e-10 (north_star's tolerance for Cl).
+    """
+    import torch.distributed as dist
+
+    cfg = PARITY_CFG
+    niter = min(args.niter, 1)
+    out = []
+    for r, w in ((rank, world), (0, 1)):
+        pipe = Pipeline(cfg, niter, r, w, torch, hb)
+        pipe.alloc_outputs()
+        pipe.step(dict.fromkeys(["map_ms", "norm_ms", "sht_ms", "cl_ms", "fft_ms", "leg_ana_ms", "leg_syn_ms", "leg_ana_flops"], 0.0))
+        torch.cuda.synchronize()
+        out.append(pipe.cl.cpu().numpy())
+        if pipe.dist is not None:
+            pipe.dist.release()
+        del pipe
+    torch.cuda.empty_cache()
+    cl_n, cl_1 = out
+    auto = np.sqrt(np.abs(np.einsum("iil->il", cl_1)))
+    norm = auto[:, None, :] * auto[None, :, :]
+    iu = np.triu_indices(cl_1.shape[0])
+    lmin = 2
+    err = float((np.abs(cl_n - cl_1)[iu][:, lmin:] / norm[iu][:, lmin:]).max())
+    t = torch.tensor([err], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    err = float(t.item())
+    res = {"max_norm_err": err, "tolerance": 1e-10, "nside": cfg["nside"], "lmax": cfg["lmax"], "components": int(cl_1.shape[0]),
+           "niter": niter, "checksum_n_gpu": checksum_matrix(cl_n), "checksum_1_gpu": checksum_matrix(cl_1)}
+    if not err <= 1e-10:
+        raise SystemExit(f"multi-GPU parity check failed: {json.dumps(res)}")
+    return res
+
+
+def run_c5(args, rank, world, local, torch, hb):
+    """
+    BASELINE.json config 5: nside 8192, lmax 16384, spin-2 map2alm of 40 (Q, U) maps -- SHT only.  The fields are
+    independent, so they are sharded over the ranks (no collective on the data path); each rank transforms its
+    fields in Legendre batches of `--c5-batch` fields drawn on the device.  One step = all 40 fields once.
+    """
+    cfg = C5
+    nside, lmax = cfg["nside"], cfg["lmax"]
+    npix, nalm = 12 * nside * nside, (lmax + 1) * (lmax + 2) // 2
+    mine = list(range(rank, cfg["fields"], world))
+    nb = max(1, min(args.c5_batch, 4))
+    ctx = hb.get_context(local)
+    ctx.set_timing(True)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    fp64_peak = ctx.fp64_peak()
+    dev = torch.device("cuda")
+    maps = torch.empty(2 * nb, npix, device=dev, dtype=torch.float64)
+    alm = torch.empty(2 * nb, nalm, device=dev, dtype=torch.complex128)
+    from heracles_b200 import _lib
+
+    def one_pass(timed):
+        tot = dict(ms=0.0, leg=0.0, fft=0.0, flops=0.0, check=0.0)
+        for b0 in range(0, len(mine), nb):
+            fields = mine[b0:b0 + nb]
+            n = 2 * len(fields)
+            for i, f in enumerate(fields):  # seeds 0..39 (SURVEY 8(d)); generation is not part of the transform
+                g = torch.Generator(device=dev)
+                g.manual_seed(f)
+                maps[2 * i:2 * i + 2].normal_(generator=g)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record()
+                _lib.check(ctx.lib.hcu_map2alm(ctx.handle, nside, lmax, 2, n, maps.data_ptr(), npix, None, None, args.niter,
+                                               None, alm.data_ptr(), nalm))
+                e1.record()
+            e1.synchronize()
+            ms = ctx.sht_timing()
+            rec, acc = ctx.sht_work()
+            tot["ms"] += e0.elapsed_time(e1)
+            tot["leg"] += ms[1]
+            tot["fft"] += ms[0] + ms[3]
+            tot["flops"] += legendre_flops(2, n, rec, acc)
+            tot["check"] += float((alm[:n].real ** 2 + alm[:n].imag ** 2).sum().item())
+        return tot
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_pass(False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launch_count()
+    barrier()
+    acc = dict(ms=0.0, leg=0.0, fft=0.0, flops=0.0, check=0.0)
+    for _ in range(args.steps):
+        t = one_pass(True)
+        for k in acc:
+            acc[k] += t[k]
+    barrier()
+    clocks = sampler.stop()
+    l1 = ctx.launch_count()
+    ms = acc["ms"]
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        t = torch.tensor([acc["check"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        acc["check"] = float(t.item())
+    ms_per_step = ms / args.steps
+    nominal = nalm * (2 * nside) * (12 + 16 * nb) * (1 + 2 * args.niter) * (cfg["fields"] / nb)
+    leg_tf = acc["flops"] / max(acc["leg"], 1e-9) * 1e3 / 1e12
+    line = {
+        "metric": "sht_seconds_per_run", "value": ms_per_step / 1e3, "unit": "s/run", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C5: {cfg['text']}", "nside": nside, "lmax": lmax, "fields": cfg["fields"], "niter": args.niter,
+                   "fields_per_batch": nb, "sharding": "fields over ranks, no data-path collective",
+                   "l2": "inputs larger than L2 (6.4 GB per map); no flush needed"},
+        "sht_fp64_tflops": nominal / (ms_per_step * 1e-3) / 1e12,
+        "sht_fp64_tflops_note": "nominal Legendre flops of SURVEY 8(d) (full triangle x all ring pairs) / wall time of the whole transform, all ranks",
+        "stage_ms_per_step_rank0": {"legendre_ms": acc["leg"] / args.steps, "fft_ms": acc["fft"] / args.steps},
+        "roofline": {"kernel": "legendre_analysis2_kernel", "bound": "tensor", "achieved": leg_tf, "peak": fp64_peak / 1e12,
+                     "unit": "TFLOP/s", "frac": leg_tf / (fp64_peak / 1e12), "traffic": None,
+                     "peak_source": "DFMA microkernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)"},
+        "gpu_launches": int((l1[0] - l0[0]) + (l1[1] - l0[1])), "clocks": clocks, "checksum": acc["check"],
+        "e2e": None,
+    }
+    if rank == 0:
+        print(json.dumps(line))
 
 
 def main():
@@ -548,6 +806,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-full", action="store_true",
+                    help="--impl reference: run the WHOLE configuration on the CPU (C1 / C2 only), nothing extrapolated")
+    ap.add_argument("--c5-batch", type=int, default=4, help="--config C5: spin-2 fields per Legendre batch")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -567,9 +828,15 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.config == "C5":
+        run_c5(args, rank, world, local, torch, hb)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     free, total_mem = torch.cuda.mem_get_info()
     cfg_name = pick_config(args.config, free)
     cfg = CONFIGS[cfg_name]
+    dist_parity = dist_parity_check(args, rank, world, torch, hb) if world > 1 else None
 
     pipe = Pipeline(cfg, args.niter, rank, world, torch, hb)
     pipe.alloc_outputs()
@@ -630,7 +897,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    checksum = float(pipe.cl.sum().item())
+    checksum = checksum_matrix(pipe.cl.cpu().numpy())
 
     # roofline of the dominant kernel and of the HBM-bound scatter
     peaks = {}
@@ -668,13 +935,7 @@ def main():
         "metric": METRIC, "value": ms_per_step / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {
-            "workload": f"{cfg_name}: {cfg['text']}", "nside": cfg["nside"], "lmax": cfg["lmax"],
-            "fields": cfg["nbins"] * (2 if cfg["she"] else 1), "rows": cfg["rows"] * cfg["nbins"], "niter": args.niter,
-            "spectra": pipe.ncomp * (pipe.ncomp + 1) // 2,
-            "pages": f"{pipe.pages} pages of {pipe.page_rows} rows per bin cycling a pool of {pipe.pool} distinct pages",
-            "l2": "inputs larger than L2 (catalogue and maps are GBs); no flush needed",
-        },
+        "config": bench_config(cfg_name, cfg, args.niter),
         "stage_ms_per_step": {k: stats[k] / args.steps for k in ("map_ms", "norm_ms", "sht_ms", "cl_ms", "fft_ms", "leg_ana_ms", "leg_syn_ms")},
         "sht_fp64_tflops_nominal": nominal_sht_flops(cfg, args.niter) / (stats["sht_ms"] / args.steps * 1e-3) / 1e12 if stats["sht_ms"] else None,
         "roofline": roofline, "roofline_map_values": roofline_map,
@@ -684,6 +945,7 @@ def main():
     }
     if pipe.dist is not None:
         line["dist_stage_ms_per_rank"] = dist_stage
+        line["dist_parity"] = dist_parity
 
     # end to end through the plugin API, host pages
     if rank == 0:

@@ -60,6 +60,9 @@ SIGNATURES = {
     "hcu_phase2alm": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_i64]),
     "hcu_alm2cl": (c_int, [c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_int, c_int, c_vp]),
     "hcu_alm2cl_mslice": (c_int, [c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),
+    "hcu_map_page": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "hcu_reorder": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int]),
+    "hcu_set_timing": (c_int, [c_vp, c_int]),
     "hcu_last_sht_timing": (c_int, [c_vp, ctypes.POINTER(ctypes.c_float * 4)]),
     "hcu_last_sht_work": (c_int, [c_vp, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),
     "hcu_measure_fp64_peak": (c_int, [c_vp, ctypes.POINTER(c_dbl)]),
@@ -178,6 +181,10 @@ class Context:
         n = c_i64(0)
         check(self.lib.hcu_bad_rows(self.handle, ctypes.byref(n)))
         return n.value
+
+    def set_timing(self, enabled: bool = True) -> None:
+        """CUDA-event timing of the SHT stages (costs a host wait per Legendre batch; off by default)"""
+        check(self.lib.hcu_set_timing(self.handle, 1 if enabled else 0))
 
     def sht_timing(self):
         arr = (ctypes.c_float * 4)()

@@ -377,6 +377,56 @@ static bool valid_nside(i64 nside) {
   return nside >= 1 && nside <= (1 << 24) && (nside & (nside - 1)) == 0;
 }
 
+int hcu_launch_map_page(hcu_ctx *ctx, i64 nside, int scheme, const double *lon, const double *lat, const double *w,
+                        const double *g1, const double *g2, i64 n, double *pos, double *she, i64 she_stride,
+                        double *stats);
+
+extern "C" int hcu_map_page(hcu_ctx *ctx, int64_t nside, int scheme, const double *lon, const double *lat,
+                            const double *w, const double *g1, const double *g2, int64_t n, double *pos,
+                            double *she, int64_t she_stride, double *stats) {
+  HCU_ARG(ctx, "ctx");
+  HCU_ARG(valid_nside(nside), "nside must be a power of two");
+  HCU_ARG(scheme == HCU_RING || scheme == HCU_NEST, "scheme");
+  HCU_ARG(n >= 0, "n >= 0");
+  if (n == 0) return HCU_OK;
+  HCU_ARG(lon && lat && (pos || she), "null pointer");
+  HCU_ARG(!she || (g1 && g2), "shear map without shear columns");
+  HCU_ARG(!pos || dev_accessible(ptr_kind(pos)), "pos must be device or managed memory");
+  HCU_ARG(!she || dev_accessible(ptr_kind(she)), "she must be device or managed memory");
+  HCU_ARG(!stats || dev_accessible(ptr_kind(stats)), "stats must be device or managed memory");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  const double *col[5] = {lon, lat, w, she ? g1 : nullptr, she ? g2 : nullptr};
+  PtrKind kind[5];
+  bool direct = true;
+  for (int c = 0; c < 5; ++c) {
+    kind[c] = col[c] ? ptr_kind(col[c]) : PK_DEVICE;
+    direct = direct && dev_accessible(kind[c]);
+  }
+  if (direct) return hcu_launch_map_page(ctx, nside, scheme, lon, lat, w, col[3], col[4], n, pos, she, she_stride, stats);
+  HCU_CHECK(ensure_slots(ctx));
+  for (i64 r0 = 0; r0 < n; r0 += hcu_ctx::SLOT_ROWS) {
+    const i64 nr = std::min<i64>(hcu_ctx::SLOT_ROWS, n - r0);
+    hcu_stage_slot &s = ctx->slot[ctx->next_slot];
+    ctx->next_slot = (ctx->next_slot + 1) % hcu_ctx::NSLOT;
+    if (s.used) HCU_CUDA(cudaEventSynchronize(s.done));
+    const double *d[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int c = 0; c < 5; ++c)
+      if (col[c]) HCU_CHECK(stage_column(ctx, s, c, col[c], kind[c], r0, nr, &d[c]));
+    HCU_CUDA(cudaEventRecord(s.ready, ctx->copy_stream));
+    HCU_CUDA(cudaStreamWaitEvent(ctx->stream, s.ready, 0));
+    HCU_CHECK(hcu_launch_map_page(ctx, nside, scheme, d[0], d[1], d[2], d[3], d[4], nr, pos, she, she_stride, stats));
+    HCU_CUDA(cudaEventRecord(s.done, ctx->stream));
+    s.used = true;
+  }
+  return HCU_OK;
+}
+
+extern "C" int hcu_set_timing(hcu_ctx *ctx, int enabled) {
+  HCU_ARG(ctx, "ctx");
+  ctx->timing = enabled != 0;
+  return HCU_OK;
+}
+
 extern "C" int hcu_map_values(hcu_ctx *ctx, int64_t nside, int scheme, const double *lon,
                               const double *lat, const double *values,
                               int64_t value_stride, int nv, int64_t n, double *maps,

@@ -57,7 +57,7 @@ void hcu_set_error(const char *fmt, ...);
 
 // up to HCU_MAX_BATCH row pointers passed to kernels by value (maps or alm rows
 // of one transform batch need not be contiguous in memory)
-#define HCU_MAX_BATCH 12
+#define HCU_MAX_BATCH 16
 struct hcu_ptrs {
   double *p[HCU_MAX_BATCH];
 };
@@ -108,7 +108,7 @@ struct hcu_ctx {
   // staging for pageable host pages
   static const int NSLOT = 3;
   static const i64 SLOT_ROWS = 1 << 19;
-  static const int SLOT_COLS = 4; // lon, lat, up to 2 value rows
+  static const int SLOT_COLS = 5; // lon, lat, up to 3 more columns (hcu_map_values: 2 value rows; hcu_map_page: w, g1, g2)
   hcu_stage_slot slot[NSLOT];
   int next_slot = 0;
   unsigned long long *bad_rows = nullptr; // device counter
@@ -121,6 +121,7 @@ struct hcu_ctx {
   // timing
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float sht_ms[4] = {0, 0, 0, 0};
+  bool timing = false;             // hcu_set_timing: CUDA events (and a host wait per batch) around the SHT stages
   double *work_counters = nullptr; // device [2]
 };
 

@@ -36,8 +36,8 @@ bool valid_nside(i64 nside) {
 
 int check_sht_args(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps) {
   HCU_ARG(ctx, "ctx");
-  HCU_ARG(valid_nside(nside) && nside <= 4096,
-          "nside must be a power of two <= 4096 (polar-cap FFT tile limit)");
+  HCU_ARG(valid_nside(nside) && nside <= 8192,
+          "nside must be a power of two <= 8192 (polar-cap FFT: Bluestein length 2 x 8192)");
   HCU_ARG(lmax >= 0 && lmax <= 4 * nside, "0 <= lmax <= 4 nside");
   if (spin != 0 && spin != 2) {
     hcu_set_error("spin-%d maps not yet supported", spin);
@@ -69,13 +69,16 @@ struct StageTimer {
   hcu_ctx *ctx;
   cudaEvent_t a, b;
   float *acc;
+  // only when hcu_set_timing enabled it: collect() waits on the host after every batch
   StageTimer(hcu_ctx *c, int i, float *dst) : ctx(c), a(c->ev[i]), b(c->ev[i + 1]), acc(dst) {
-    cudaEventRecord(a, ctx->stream);
+    if (ctx->timing) cudaEventRecord(a, ctx->stream);
   }
-  void stop() { cudaEventRecord(b, ctx->stream); }
+  void stop() {
+    if (ctx->timing) cudaEventRecord(b, ctx->stream);
+  }
   void collect() {
     float t = 0;
-    if (cudaEventSynchronize(b) == cudaSuccess && cudaEventElapsedTime(&t, a, b) == cudaSuccess)
+    if (ctx->timing && cudaEventSynchronize(b) == cudaSuccess && cudaEventElapsedTime(&t, a, b) == cudaSuccess)
       *acc += t;
   }
 };

@@ -765,13 +765,14 @@ static int legendre_nw() {
   static int nw = -1;
   if (nw < 0) {
     const char *e = getenv("HCU_LEGENDRE_NW");
-    nw = (e && atoi(e) == 12) ? 12 : 16;
+    nw = (e && atoi(e) == 12) ? 12 : (e && atoi(e) == 8) ? 8 : 16;
   }
   return nw;
 }
 
 // components one Legendre launch takes: 8 spin-0 maps or 4 spin-2 fields (Q, U rows)
-int hcu_legendre_batch(int spin) { (void)spin; return 8; }
+// (HCU_LEGENDRE_NW=8: experimental 16-component analysis batches, analysis only)
+int hcu_legendre_batch(int spin) { (void)spin; return (legendre_gen() == 2 && legendre_nw() == 8) ? 16 : 8; }
 
 int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c) {
   const i64 nalm = (i64)(c->lmax + 1) * (c->lmax + 2) / 2;

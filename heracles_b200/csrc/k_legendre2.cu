@@ -29,6 +29,8 @@
 // Analysis flush: per sub-chunk every warp parks its 16 l x 16 column partial tile in a double-buffered
 // shared tile; it is reduced over the warps one sub-chunk LATER (split-phase mbarrier, nobody waits)
 // and added to alm with one RED.ADD.F64 per output (x s_l x fl[l]).
+#include <type_traits>
+
 #include "legendre_common.cuh"
 
 namespace {
@@ -52,11 +54,15 @@ __device__ __forceinline__ double xor_hi(double v, unsigned bits) {
 // ------------------------------------------------------------------------------------------
 // one recursion chain per lane
 // ------------------------------------------------------------------------------------------
-template <int SPIN>
+// XSIGN: how the lambda^{-2} chain (A_l x - B_l) differs from the lambda^{+2} chain (A_l x + B_l):
+//   true   the sign bit of B_l is flipped in every step (one LOP3 per step)
+//   false  the chain runs the lambda^{+2} code on x' = -x: q'_l = (-1)^l q_l obeys q'_{l+1} = (A_l x' + B_l) q'_l - q'_{l-1};
+//          the consumer folds (-1)^l into its operand fragments (analysis: the ring Fourier coefficients)
+template <int SPIN, bool XSIGN = true>
 struct Chain {
   double prev, cur, x;
   int e;
-  unsigned sgn;    // spin 2: sign bit of the B_l term (0: lambda^{+2}, 0x80000000: lambda^{-2})
+  unsigned sgn;    // spin 2, XSIGN: sign bit of the B_l term (0: lambda^{+2}, 0x80000000: lambda^{-2})
   unsigned o4[4];  // byte offset of the 128-bit store of step group q inside a tile[t]
 
   __device__ __forceinline__ void init(int lane) {
@@ -66,30 +72,55 @@ struct Chain {
 #pragma unroll
     for (int q = 0; q < 4; ++q) o4[q] = 8u * (unsigned)(lane * 8 + 2 * (q ^ swzf(lane)));
   }
-  // steps 4q .. 4q+3 of the sub-chunk being produced; tn = shared address of its tile
-  __device__ __forceinline__ void step4(const double *cf, unsigned tn, int q, int ok) {
-    double v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      v[u] = cur;
-      double ax;
-      if (SPIN == 0) {
-        ax = cf[4 * q + u] * x;
-      } else {
-        const double2 c2 = reinterpret_cast<const double2 *>(cf)[4 * q + u];
-        ax = fma(c2.x, x, xor_hi(c2.y, sgn));
-      }
-      const double nw = fma(ax, cur, -prev);
-      prev = cur;
-      cur = nw;
-    }
-    sts2_pred(tn + o4[q], v[0], v[2], ok);          // even steps -> tile[0]
-    sts2_pred(tn + 2048u + o4[q], v[1], v[3], ok);  // odd steps  -> tile[1]
+  // The coefficients of a step are fetched from shared memory TWO steps before they are used (c0 / c1 roll),
+  // so that the in-order warp never waits for the load; v[] collects the four values of a step group.
+  using CT = typename std::conditional<SPIN == 0, double, double2>::type;
+  CT c0, c1;
+  double v[4];
+  __device__ __forceinline__ void begin(const double *cf) {
+    c0 = reinterpret_cast<const CT *>(cf)[0];
+    c1 = reinterpret_cast<const CT *>(cf)[1];
   }
-  // extended-exponent bookkeeping, once per sub-chunk (values grow by far less than 2^400 in 16 steps)
+  // step u (0..15) of the sub-chunk being produced; tn = shared address of its tile
+  __device__ __forceinline__ void step(const double *cf, unsigned tn, int u, int ok) {
+    const CT c = (u & 1) ? c1 : c0;
+    if (u + 2 < SL) {
+      if (u & 1)
+        c1 = reinterpret_cast<const CT *>(cf)[u + 2];
+      else
+        c0 = reinterpret_cast<const CT *>(cf)[u + 2];
+    }
+    v[u & 3] = cur;
+    double ax;
+    if constexpr (SPIN == 0) {
+      ax = c * x;
+    } else {
+      ax = XSIGN ? fma(c.x, x, xor_hi(c.y, sgn)) : fma(c.x, x, c.y);
+    }
+    const double nw = fma(ax, cur, -prev);
+    prev = cur;
+    cur = nw;
+    if ((u & 3) == 3) {
+      const int q = u >> 2;
+      sts2_pred(tn + o4[q], v[0], v[2], ok);          // even steps -> tile[0]
+      sts2_pred(tn + 2048u + o4[q], v[1], v[3], ok);  // odd steps  -> tile[1]
+    }
+  }
+  __device__ __forceinline__ void step4(const double *cf, unsigned tn, int q, int ok) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) step(cf, tn, 4 * q + u, ok);
+  }
+  __device__ __forceinline__ void sub16(const double *cf, unsigned tn, int ok) {
+    begin(cf);
+#pragma unroll
+    for (int u = 0; u < SL; ++u) step(cf, tn, u, ok);
+  }
+  // extended-exponent bookkeeping, once per sub-chunk (values grow by far less than 2^400 in 16 steps).
+  // The magnitude test reads the exponent field on the integer pipe: a DSETP would queue behind the DMMAs.
   __device__ __forceinline__ void end_sub() {
     if (__any_sync(0xffffffffu, e < 0)) {
-      if (e < 0 && fmax(fabs(cur), fabs(prev)) >= TWO_P200) {
+      const int ec = __double2hiint(cur) & 0x7ff00000, ep = __double2hiint(prev) & 0x7ff00000;
+      if (e < 0 && max(ec, ep) >= 0x4c700000) {  // |.| >= 2^200
         cur *= TWO_M400;
         prev *= TWO_M400;
         e += SCALE_STEP;
@@ -126,8 +157,8 @@ struct Setup2 {
 };
 
 // CTA geometry, ring constants and recursion start values.  RW = ring pairs per warp, R = per CTA.
-template <int SPIN, int NW>
-__device__ __forceinline__ bool setup2(const LegArgs &a, Setup2 &s, Chain<SPIN> &ch, bool &alive, int warp, int lane) {
+template <int SPIN, int NW, bool XSIGN>
+__device__ __forceinline__ bool setup2(const LegArgs &a, Setup2 &s, Chain<SPIN, XSIGN> &ch, bool &alive, int warp, int lane) {
   constexpr int RW = SPIN == 0 ? 32 : 16;
   constexpr int R = NW * RW;
   const int ngroups = a.grp_start[a.nblk];
@@ -169,6 +200,10 @@ __device__ __forceinline__ bool setup2(const LegArgs &a, Setup2 &s, Chain<SPIN> 
     ch.prev = pick.prev;
     ch.cur = pick.cur;
     ch.e = pick.e;
+    if (!XSIGN && j == 1) {  // q'_l = (-1)^l q_l on x' = -x
+      ch.x = -ch.x;
+      if (s.l0 & 1) ch.cur = -ch.cur;
+    }
   } else {
     ch.x = 0.0;
   }
@@ -190,12 +225,13 @@ struct A2Cfg {
   static constexpr int FS = SL + 2;                       // column stride of a flush tile (conflict free)
   static constexpr int FLUSH = NW * C * FS;               // one buffer: [warp][col][FS]
   static constexpr int NOUT = SL * C;                     // outputs per sub-chunk and CTA
-  static constexpr int NSPLIT = (NT / NOUT) >= 1 ? (NT / NOUT) : 1;  // thread groups sharing the source warps
+  static constexpr int NOPT = NOUT > NT ? NOUT / NT : 1;  // outputs per thread
+  static constexpr int NSPLIT = NOUT > NT ? 1 : NT / NOUT;  // thread groups sharing the source warps of an output
   static constexpr int NSRC = NW / NSPLIT;
   static constexpr int FLAG_OFF = NW * WARP + 2 * FLUSH;  // 2 x NW ints (padded to 16), then two mbarriers
   static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(FLAG_OFF + 16 + 2);
   static_assert(NW % NSPLIT == 0, "source warps must split evenly");
-  static_assert(NT >= NOUT || NSPLIT == 1, "flush mapping");
+  static_assert(NOUT % NT == 0 || NOUT < NT, "flush mapping");
 };
 
 template <int SPIN, int NW, int NBLK>
@@ -204,9 +240,9 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_analysis2_kernel(LegArgs 
   extern __shared__ __align__(16) double smem_d[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Setup2 st;
-  Chain<SPIN> ch;
+  Chain<SPIN, false> ch;
   bool alive;
-  if (!setup2<SPIN, NW>(a, st, ch, alive, warp, lane)) return;
+  if (!setup2<SPIN, NW, false>(a, st, ch, alive, warp, lane)) return;
   const int lmax = a.lmax;
   const i64 cbase = st.cbase;
   double *tiles = smem_d + warp * K::WARP;
@@ -261,7 +297,9 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_analysis2_kernel(LegArgs 
               X = -prow[f * 8 + oP];
               Y = sM * prow[f * 8 + oM];
             }
-            bf[kk][t][nb] = jj == 0 ? 0.5 * (X + Y) : 0.5 * (X - Y);
+            // the lambda^{-2} chain delivers (-1)^l lambda (see Chain): l = l0 + 16 k + 2 idx + t
+            const double sg = ((st.l0 + t) & 1) ? -0.5 : 0.5;
+            bf[kk][t][nb] = jj == 0 ? 0.5 * (X + Y) : sg * (X - Y);
           }
         }
       }
@@ -272,39 +310,55 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_analysis2_kernel(LegArgs 
   const int a_off0 = lam_off(fa, fb), a_off1 = lam_off(4 + fa, fb) - 32;
   int n_rec = 0, n_acc = 0;
 
-  // flush assignment of this thread: output (lo, col) of the sub-chunk, source warps [src0, src0 + NSRC)
+  // flush assignment of this thread: NOPT outputs (lo, col) of the sub-chunk, source warps [src0, src0 + NSRC)
   const bool f_active = threadIdx.x < K::NSPLIT * K::NOUT;
-  const int f_o = threadIdx.x % K::NOUT;
-  const int f_lo = f_o & (SL - 1);        // l - lsub
-  const int f_col = f_o / SL;
-  const int f_src0 = (threadIdx.x / K::NOUT) * K::NSRC;
+  const int f_lo = threadIdx.x & (SL - 1);  // l - lsub (the same for all outputs of the thread)
+  const int f_src0 = (K::NOUT > K::NT) ? 0 : (threadIdx.x / K::NOUT) * K::NSRC;
   const int f_pos = (f_lo & 1) * 8 + (f_lo >> 1);  // position inside a flush column: [t][idx]
-  int f_row, f_ri;
-  if (SPIN == 0) {
-    f_row = f_col >> 1;
-    f_ri = f_col & 1;
-  } else {
-    f_row = 2 * (f_col >> 2) + ((f_col >> 1) & 1);
-    f_ri = f_col & 1;
+  int f_colv[K::NOPT];
+  double *f_dst[K::NOPT];
+  bool f_any = false;
+#pragma unroll
+  for (int i = 0; i < K::NOPT; ++i) {
+    const int col = ((threadIdx.x + i * K::NT) % K::NOUT) / SL;
+    int row, ri;
+    if (SPIN == 0) {
+      row = col >> 1;
+      ri = col & 1;
+    } else {
+      row = 2 * (col >> 2) + ((col >> 1) & 1);
+      ri = col & 1;
+    }
+    f_colv[i] = col;
+    f_dst[i] = (f_active && row < a.ncomp) ? a.alm.p[row] + 2 * cbase + ri : nullptr;
+    f_any = f_any || f_dst[i] != nullptr;
   }
-  const bool f_use = f_active && f_row < a.ncomp;
-  double *f_dst = f_use ? a.alm.p[f_row] + 2 * cbase + f_ri : nullptr;
 
   // the reduction of sub-chunk s over the warps is deferred to the end of sub-chunk s + 1, so that nobody
   // waits at a barrier: partial tiles and flags are double buffered, mbar[s & 1] counts the warps
-  auto reduce_sub = [&](int s, int f_l, double f_sc) {
+  auto reduce_sub = [&](int s, int f_l, double f_sc, double f_fl) {
     mbar_wait(mbar + (s & 1), (s >> 1) & 1);
-    if (!f_use || f_l > lmax) return;
+    if (!f_any || f_l > lmax) return;
     const int *fl = flags + (s & 1) * 16;
     int any = 0;
 #pragma unroll
     for (int w = 0; w < K::NSRC; ++w) any |= fl[f_src0 + w];
     if (!any) return;
-    const double *fbuf = flush + (s & 1) * K::FLUSH + f_src0 * (K::C * K::FS) + f_col * K::FS + f_pos;
-    double sum = 0.0;
+    const double sc = f_sc * f_fl;
 #pragma unroll
-    for (int w = 0; w < K::NSRC; ++w) sum += fbuf[w * (K::C * K::FS)];
-    atomicAdd(f_dst + 2 * (i64)f_l, sum * f_sc);
+    for (int i = 0; i < K::NOPT; ++i) {
+      if (f_dst[i] == nullptr) continue;
+      const double *fbuf = flush + (s & 1) * K::FLUSH + f_src0 * (K::C * K::FS) + f_colv[i] * K::FS + f_pos;
+      // pairwise tree: the additions queue behind other warps' DMMAs, keep the dependent chain short
+      double part[K::NSRC];
+#pragma unroll
+      for (int w = 0; w < K::NSRC; ++w) part[w] = fbuf[w * (K::C * K::FS)];
+#pragma unroll
+      for (int st = 1; st < K::NSRC; st *= 2)
+#pragma unroll
+        for (int w = 0; w + st < K::NSRC; w += 2 * st) part[w] += part[w + st];
+      atomicAdd(f_dst[i] + 2 * (i64)f_l, part[0] * sc);
+    }
   };
 
   // ---- prologue: coefficients and tile of sub-chunk 0 ----
@@ -315,14 +369,20 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_analysis2_kernel(LegArgs 
   bool live_cur = false, live_nxt = false;
   if (warp_alive) {
     live_cur = __any_sync(0xffffffffu, alive && ch.e == 0);
-    const int ok = ch.e == 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) ch.step4(coefs, tile_s, q, ok);
+    ch.sub16(coefs, tile_s, ch.e == 0);
     ch.end_sub();
     n_rec += 1;
   }
-  int f_l_prev = 0;
-  double f_sc_prev = 0.0;
+  // scale (and window) of this thread's flush outputs of the sub-chunk whose reduction is pending
+  int f_l = st.l0 + f_lo;
+  double f_sc = 0.0, f_fl = 1.0;
+  auto load_scale = [&](int lsub) {
+    f_l = lsub + f_lo;
+    if (f_any) {
+      f_sc = ldg_pin(a.scale + cbase + min(f_l, lmax));
+      if (a.fl) f_fl = ldg_pin(a.fl + min(f_l, lmax));
+    }
+  };
 
   for (int s2 = 0; s2 < st.nsub; s2 += 2) {
 #pragma unroll
@@ -333,13 +393,6 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_analysis2_kernel(LegArgs 
       const double *tcur = tiles + sb * K::TILE;
       const unsigned tn = tile_s + (unsigned)((1 - sb) * K::TILE * 8);
       const double *ccur = coefs + (1 - sb) * (SL * 2);
-      // scale of this thread's flush output, fetched a sub-chunk's worth of work ahead
-      const int f_l = lsub + f_lo;
-      double f_sc = 0.0;
-      if (f_use) {
-        f_sc = ldg_pin(a.scale + cbase + min(f_l, lmax));
-        if (a.fl) f_sc *= ldg_pin(a.fl + min(f_l, lmax));
-      }
       coef_wait();
       __syncwarp();  // tile `sidx` and the coefficients of sub-chunk sidx + 1 are in place
       double acc[2][NBLK][2];
@@ -347,38 +400,74 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_analysis2_kernel(LegArgs 
       for (int t = 0; t < 2; ++t)
 #pragma unroll
         for (int nb = 0; nb < NBLK; ++nb) acc[t][nb][0] = acc[t][nb][1] = 0.0;
+      // The per-sub-chunk chores -- the deferred reduction of sub-chunk sidx - 1, the scale loads for sub-chunk
+      // sidx and the coefficient prefetch for sub-chunk sidx + 2 -- are issued BETWEEN the DMMAs of a live
+      // sub-chunk: a warp cannot issue its next DMMA for 16 clocks anyway, and these instructions need no FP64 pipe.
+      auto chore = [&](int which) {
+        if (which == 0) {
+#ifndef HCU_EXP_NOFLUSH
+          if (sidx > 0) reduce_sub(sidx - 1, f_l, f_sc, f_fl);
+#endif
+        } else if (which == 1) {
+          load_scale(lsub);
+        } else {
+          // the recursion always runs one sub-chunk ahead (the one past the end is harmless: its
+          // coefficients are zero and nothing reads it)
+          if (warp_alive) stage_coef2<SPIN>(coefs + sb * (SL * 2), a, cbase, lsub + 2 * SL, lane);
+          else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+      };
       if (warp_alive) {
-        // the recursion always runs one sub-chunk ahead (the one past the end is harmless: its
-        // coefficients are zero and nothing reads it)
-        stage_coef2<SPIN>(coefs + sb * (SL * 2), a, cbase, lsub + 2 * SL, lane);
         live_nxt = __any_sync(0xffffffffu, alive && ch.e == 0);
         const int ok = ch.e == 0;
         if (sidx + 1 < st.nsub) n_rec += 1;
         if (live_cur) {
           n_acc += 1;
           // DMMAs of sub-chunk sidx interleaved with the recursion of sub-chunk sidx + 1
+          ch.begin(ccur);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
-#ifndef HCU_EXP_NOREC
-            if (!(kk & 1)) ch.step4(ccur, tn, kk >> 1, ok);
-#endif
             const double *ta = tcur + ((kk & 1) ? a_off1 : a_off0) + 32 * kk;
             const double a0 = ta[0], a1 = ta[256];
+#ifndef HCU_EXP_NOREC
+            ch.step(ccur, tn, 2 * kk, ok);
+#endif
 #pragma unroll
             for (int nb = 0; nb < NBLK; ++nb) dmma(acc[0][nb][0], acc[0][nb][1], a0, bf[kk][0][nb]);
+#ifndef HCU_EXP_NOREC
+            ch.step(ccur, tn, 2 * kk + 1, ok);
+#endif
 #pragma unroll
             for (int nb = 0; nb < NBLK; ++nb) dmma(acc[1][nb][0], acc[1][nb][1], a1, bf[kk][1][nb]);
+            if (kk == 1) chore(2);
+            if (kk == 3) chore(0);
+            if (kk == 5) chore(1);
           }
         } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) ch.step4(ccur, tn, q, ok);
+          chore(2);
+          ch.sub16(ccur, tn, ok);
+          chore(0);
+          chore(1);
         }
         ch.end_sub();
+      } else {
+        chore(2);
+        chore(0);
+        chore(1);
       }
-      // ---- first the deferred reduction of the previous sub-chunk, then park this one's partial tile ----
-      if (sidx > 0) reduce_sub(sidx - 1, f_l_prev, f_sc_prev);
-      f_l_prev = f_l;
-      f_sc_prev = f_sc;
+#ifdef HCU_EXP_NOFLUSH
+      {  // ablation: no partial tiles, no barrier, no reduction (results are wrong on purpose)
+        double ssum = f_sc * f_fl;
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int nb = 0; nb < NBLK; ++nb) ssum += acc[t][nb][0] + acc[t][nb][1];
+        f_sc += ssum;
+        live_cur = warp_alive ? live_nxt : false;
+        continue;
+      }
+#endif
+      // ---- park this sub-chunk's partial tile (its reduction happens during the NEXT sub-chunk) ----
       if (lane == 0) flags[sb * 16 + warp] = live_cur ? 1 : 0;
       {  // a warp without live values parks zeros: the reducers add all source warps unconditionally
         double *o = flush + sb * K::FLUSH + warp * (K::C * K::FS);
@@ -396,7 +485,11 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_analysis2_kernel(LegArgs 
       live_cur = warp_alive ? live_nxt : false;
     }
   }
-  reduce_sub(st.nsub - 1, f_l_prev, f_sc_prev);
+#ifdef HCU_EXP_NOFLUSH
+  if (f_sc == 1.2345e-300) atomicAdd(a.alm.p[0], f_sc);
+#else
+  reduce_sub(st.nsub - 1, f_l, f_sc, f_fl);
+#endif
   if (lane == 0 && a.work && n_rec > 0) {
     atomicAdd(a.work, n_rec * (double)(K::RW * SL));
     atomicAdd(a.work + 1, n_acc * (double)(K::RW * SL));
@@ -415,7 +508,10 @@ struct S2Cfg {
   static constexpr int NROW = SPIN == 0 ? 4 * NBLK : 8;   // alm rows (components) staged per l
   static constexpr int BSTR = 20;                         // row stride of the a_lm tile: 4 (mod 16), >= 2 NROW
   static constexpr int TILE = 2 * 256;
-  static constexpr int BT = LC * BSTR;                    // one a_lm tile: [t][16][BSTR]
+  static constexpr int TPAD = 2;                          // doubles between the two t-blocks: rows r and 16 + r of a tile
+                                                          // are touched by neighbouring lanes (bank conflict free with it)
+  static constexpr int TSTR = 16 * BSTR + TPAD;           // stride of a t-block
+  static constexpr int BT = 2 * TSTR;                     // one a_lm tile: [t][16][BSTR]
   static constexpr int WARP = 2 * TILE + 2 * SL * 2 + 2 * BT;
   static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(NW * WARP);
   static_assert(SPIN == 0 || NBLK == 2, "spin 2 synthesis uses the (+2a | -2a) two-block column layout");
@@ -428,9 +524,9 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_synthesis2_kernel(LegArgs
   extern __shared__ __align__(16) double smem_d[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Setup2 st;
-  Chain<SPIN> ch;
+  Chain<SPIN, true> ch;
   bool alive;
-  const bool active = setup2<SPIN, NW>(a, st, ch, alive, warp, lane);
+  const bool active = setup2<SPIN, NW, true>(a, st, ch, alive, warp, lane);
   double *dst = a.phase_out + st.poff + ((i64)st.mi * st.nrp_b + st.row0) * a.ncomp * 4;
   if (!active) {  // every output row must be defined
     for (int i = threadIdx.x; i < st.nrows * a.ncomp * 4; i += K::NT) dst[i] = 0.0;
@@ -466,7 +562,7 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_synthesis2_kernel(LegArgs
       for (int nb = 0; nb < NBLK; ++nb) acc[i][mb][nb][0] = acc[i][mb][nb][1] = 0.0;
 
   // a_lm of one chunk: lane = l row of the chunk; row of the tile: (lane & 1) * 16 + (lane >> 1) = [t][idx]
-  const int brow = ((lane & 1) * 16 + (lane >> 1)) * K::BSTR;
+  const int brow = (lane & 1) * K::TSTR + (lane >> 1) * K::BSTR;
   auto fetch_alm = [&](int chk) {  // cp.async of the raw rows (zero fill past lmax), plus s_l into the last slot
     double *bt = btiles + (chk & 1) * K::BT + brow;
     const int l = st.l0 + chk * LC + lane;
@@ -525,9 +621,7 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_synthesis2_kernel(LegArgs
   stage_coef2<SPIN>(coefs + SL * 2, a, cbase, st.l0 + SL, lane);  // coefficients of sub-chunk 1
   {
     live_cur = __any_sync(0xffffffffu, alive && ch.e == 0);
-    const int ok = ch.e == 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) ch.step4(coefs, tile_s, q, ok);
+    ch.sub16(coefs, tile_s, ch.e == 0);
     ch.end_sub();
   }
 
@@ -548,12 +642,13 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_synthesis2_kernel(LegArgs
       live_nxt = __any_sync(0xffffffffu, alive && ch.e == 0);
       const int ok = ch.e == 0;
       if (live_cur) {
+        ch.begin(ccur);
         // k4 steps: (step parity t, half h) -> rows t*16 + sb*8 + 4h + fa of the a_lm tile, l index 4h + fa of the Lam tile
 #pragma unroll
         for (int th = 0; th < 4; ++th) {
           const int t = th >> 1, h = th & 1;
           ch.step4(ccur, tn, th, ok);
-          const double *brw = bt + (t * 16 + sb * 8 + 4 * h + fa) * K::BSTR + fb;
+          const double *brw = bt + t * K::TSTR + (sb * 8 + 4 * h + fa) * K::BSTR + fb;
           double bfr[NBLK];
 #pragma unroll
           for (int nb = 0; nb < NBLK; ++nb) bfr[nb] = brw[nb * 8];
@@ -580,8 +675,7 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_synthesis2_kernel(LegArgs
           }
         }
       } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) ch.step4(ccur, tn, q, ok);
+        ch.sub16(ccur, tn, ok);
       }
       ch.end_sub();
       live_cur = live_nxt;
@@ -665,6 +759,7 @@ int launch_synthesis2(hcu_ctx *ctx, LegArgs &a, const i64 *rp_bounds) {
 int hcu_legendre2_analysis(hcu_ctx *ctx, void *args, const i64 *rp_bounds, int spin, int ncomp, int nw) {
   LegArgs &a = *reinterpret_cast<LegArgs *>(args);
   const int nblk = (ncomp + 3) / 4 <= 1 ? 1 : 2;  // 8 output columns per n-block: 4 spin-0 maps or 2 spin-2 fields
+  if (ncomp > 8) return spin == 0 ? launch_analysis2<0, 8, 4>(ctx, a, rp_bounds) : launch_analysis2<2, 8, 4>(ctx, a, rp_bounds);
   if (spin == 0) {
     if (nw == 16) return nblk == 1 ? launch_analysis2<0, 16, 1>(ctx, a, rp_bounds) : launch_analysis2<0, 16, 2>(ctx, a, rp_bounds);
     return nblk == 1 ? launch_analysis2<0, 12, 1>(ctx, a, rp_bounds) : launch_analysis2<0, 12, 2>(ctx, a, rp_bounds);
@@ -676,6 +771,10 @@ int hcu_legendre2_analysis(hcu_ctx *ctx, void *args, const i64 *rp_bounds, int s
 int hcu_legendre2_synthesis(hcu_ctx *ctx, void *args, const i64 *rp_bounds, int spin, int ncomp, int nw) {
   LegArgs &a = *reinterpret_cast<LegArgs *>(args);
   (void)nw;
+  if (ncomp > 8) {
+    hcu_set_error("synthesis takes at most 8 components per launch");
+    return HCU_ERR_UNSUPPORTED;
+  }
   if (spin == 0) {
     const int nblk = (ncomp + 3) / 4 <= 1 ? 1 : 2;
     return nblk == 1 ? launch_synthesis2<0, 12, 1>(ctx, a, rp_bounds) : launch_synthesis2<0, 12, 2>(ctx, a, rp_bounds);

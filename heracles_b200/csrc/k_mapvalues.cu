@@ -170,6 +170,71 @@ map_values_kernel(i64 nside, int order, const double *__restrict__ lon,
   if (bad) atomicAdd(bad_rows, bad);
 }
 
+// ---------------------------------------------------------------------------
+// one catalogue page -> position map AND shear map in one pass (hcu_map_page):
+// the Positions and the Shears field of a tomographic bin read the same lon / lat / weight
+// columns (heracles/fields.py:262-271 and :420-433), so ang2pix runs once and five columns
+// instead of seven cross PCIe.  The running sums the Field layer keeps per page (ngal, wmean,
+// w2mean, var) are reduced on the device: per thread over its rows, then per warp, then one
+// atomicAdd per warp and statistic.
+// ---------------------------------------------------------------------------
+template <int NEST>
+__global__ void __launch_bounds__(256)
+map_page_kernel(i64 nside, int order, const double *__restrict__ lon, const double *__restrict__ lat,
+                const double *__restrict__ w, const double *__restrict__ g1, const double *__restrict__ g2,
+                i64 n, double *__restrict__ pos, double *__restrict__ she, i64 she_stride,
+                double *__restrict__ stats, unsigned long long *bad_rows) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  double st[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) st[k] = 0.0;
+  unsigned long long bad = 0;
+  for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const double lo = ld_stream(lon + j), la = ld_stream(lat + j);
+    const double wj = w ? ld_stream(w + j) : 1.0;
+    double a = 0.0, b = 0.0;
+    if (she) {
+      a = ld_stream(g1 + j);
+      b = ld_stream(g2 + j);
+    }
+    // CatalogPage.get raises on NaN in a requested column (catalog/base.py:114-125)
+    if (lo != lo || la != la || wj != wj || a != a || b != b) {
+      st[7] += 1.0;
+      continue;
+    }
+    const i64 pix = ang2pix_lonlat<NEST>(nside, order, lo, la);
+    if (pix < 0) {
+      ++bad;
+      continue;
+    }
+    if (pos) {
+      atomicAdd(pos + pix, wj);
+      st[0] += 1.0;
+      st[1] += wj;
+      st[2] += wj * wj;
+    }
+    if (she && wj != 0.0) {  // page.delete(page[wcol] == 0), fields.py:420-421
+      const double re = wj * a, im = wj * b;  // fields.py:426
+      atomicAdd(she + pix, re);
+      atomicAdd(she + she_stride + pix, im);
+      st[3] += 1.0;
+      st[4] += wj;
+      st[5] += wj * wj;
+      st[6] += re * re + im * im;
+    }
+  }
+  if (stats) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      double v = st[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(stats + k, v);
+    }
+  }
+  if (bad) atomicAdd(bad_rows, bad);
+}
+
 template <int NEST, int NV>
 int launch2(hcu_ctx *ctx, i64 nside, const double *lon, const double *lat,
             const double *values, i64 vstride, i64 n, double *maps, i64 mstride,
@@ -322,6 +387,21 @@ __device__ i64 xyf2ring_dev(i64 nside, i64 ix, i64 iy, int face) {
   return n_before + jp - 1;
 }
 
+// RING <-> NEST reordering of a whole map (hp.reorder): the transform works on RING maps
+__global__ void reorder_kernel(i64 nside, int order, const double *__restrict__ in, double *__restrict__ out, int to_nest) {
+  const i64 npix = 12 * nside * nside;
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;  // RING index
+  if (p >= npix) return;
+  i64 ix, iy;
+  int face;
+  ring2xyf_dev(nside, p, &ix, &iy, &face);
+  const i64 q = xyf2nest(ix, iy, face, order);
+  if (to_nest)
+    out[q] = in[p];
+  else
+    out[p] = in[q];
+}
+
 __global__ void ud_grade_kernel(i64 nside_in, const double *in, i64 nside_out,
                                 double *out) {
   const i64 npix_out = 12 * nside_out * nside_out;
@@ -394,6 +474,34 @@ int hcu_mul(hcu_ctx *ctx, double *out, const double *a, const double *b, i64 n) 
 int hcu_ud_grade_dev(hcu_ctx *ctx, i64 nside_in, const double *in, i64 nside_out, double *out) {
   i64 npix = 12 * nside_out * nside_out;
   ud_grade_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(nside_in, in, nside_out, out);
+  HCU_LAUNCH_CHECK(ctx);
+  return HCU_OK;
+}
+
+// all pointers device-accessible; see hcu_map_page
+int hcu_launch_map_page(hcu_ctx *ctx, i64 nside, int scheme, const double *lon, const double *lat, const double *w,
+                        const double *g1, const double *g2, i64 n, double *pos, double *she, i64 she_stride,
+                        double *stats) {
+  if (n <= 0) return HCU_OK;
+  const int order = ilog2_host(nside);
+  i64 blocks = (n + 255) / 256;
+  const i64 maxb = (i64)ctx->num_sms * 8;
+  if (blocks > maxb) blocks = maxb;
+  if (scheme == HCU_NEST)
+    map_page_kernel<1><<<(unsigned)blocks, 256, 0, ctx->stream>>>(nside, order, lon, lat, w, g1, g2, n, pos, she,
+                                                                  she_stride, stats, ctx->bad_rows);
+  else
+    map_page_kernel<0><<<(unsigned)blocks, 256, 0, ctx->stream>>>(nside, order, lon, lat, w, g1, g2, n, pos, she,
+                                                                  she_stride, stats, ctx->bad_rows);
+  HCU_LAUNCH_CHECK(ctx);
+  return HCU_OK;
+}
+
+extern "C" int hcu_reorder(hcu_ctx *ctx, int64_t nside, const double *in, double *out, int to_nest) {
+  HCU_ARG(ctx && in && out && in != out, "hcu_reorder: null pointer / in-place");
+  HCU_ARG(nside >= 1 && (nside & (nside - 1)) == 0, "nside must be a power of two");
+  const i64 npix = 12 * nside * nside;
+  reorder_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(nside, ilog2_host(nside), in, out, to_nest);
   HCU_LAUNCH_CHECK(ctx);
   return HCU_OK;
 }

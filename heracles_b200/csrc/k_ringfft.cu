@@ -16,6 +16,8 @@
 //   = (re+, im+, re-, im-),  + = north + south, - = north - south.
 //
 // HBM-bound: algorithmic bytes = 8 npix (map read) + 32 nrp (lmax+1) (phase write) per component.
+#include <stdlib.h>
+
 #include "hcu_common.cuh"
 
 namespace {
@@ -146,6 +148,78 @@ __global__ void bluestein_filter_kernel(int ilo, int M, double2 *bfilt, const i6
   for (int j = threadIdx.x; j < M; j += blockDim.x) out[j] = a[j];
 }
 
+// ---- sub-transforms whose Bluestein length M = 2 Mh does not fit shared memory (ring number i > 4096,
+// i.e. nside 8192): the FIRST radix-2 stage of the length-M transform is done "out of core".  A
+// decimation-in-frequency stage splits x into u[j] = x[j] + x[j + Mh] and d[j] = (x[j] - x[j + Mh]) w_M^j,
+// whose length-Mh transforms are the even and the odd frequencies -- in bit-reversed order exactly the
+// first and the second half of the length-M spectrum, so the two halves are transformed, multiplied by
+// their half of the filter and transformed back one after the other in the SAME shared tile, and the
+// last (inverse) stage x[k] = r0[k] + conj(w_M^k) r1[k] is applied while the second half is written.
+// The chirp-multiplied input is non-zero only for j < i <= Mh, so u = x and d = x w_M^j.
+__device__ __forceinline__ double2 w_big(int j, int Mh) { return expmipi((double)j / (double)Mh); }  // exp(-2 pi i j / (2 Mh))
+
+__global__ void bluestein_filter_big_kernel(int ilo, int Mh, double2 *bfilt, const i64 *off) {
+  extern __shared__ double2 smem[];
+  double2 *a = smem;
+  double2 *tw = smem + Mh;
+  const int n = ilo + blockIdx.x;
+  const int M = 2 * Mh;
+  make_twiddles(tw, Mh);
+  const double inv = 1.0 / (double)M;
+  double2 *out = bfilt + off[n];
+  for (int half = 0; half < 2; ++half) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < Mh; j += blockDim.x) {
+      // b[j] = conj(chirp(j)) / M for j < n; b[M - j] = b[j]: the second half holds x1[j] = b[Mh - j] for Mh - j < n
+      double2 x0 = make_double2(0., 0.), x1 = make_double2(0., 0.);
+      if (j < n) {
+        const double2 c = chirp(j, n);
+        x0 = make_double2(c.x * inv, -c.y * inv);
+      }
+      if (j > 0 && Mh - j < n) {
+        const double2 c = chirp(Mh - j, n);
+        x1 = make_double2(c.x * inv, -c.y * inv);
+      }
+      a[j] = half == 0 ? cadd(x0, x1) : cmul(csub(x0, x1), w_big(j, Mh));
+    }
+    __syncthreads();
+    fft_dif(a, tw, Mh);
+    for (int j = threadIdx.x; j < Mh; j += blockDim.x) out[(i64)half * Mh + j] = a[j];
+  }
+}
+
+// the convolution of one sub-sequence with the chirp filter, length M = 2 Mh:
+//   load(j)      chirp-multiplied input, j < i
+//   stash / fetch (k, v)   park the first half's result r0[k] (k < i) in global memory (same thread both times)
+//   fin(k, r)    receives r[k], k < i
+template <class Load, class Stash, class Fetch, class Fin>
+__device__ __forceinline__ void bluestein_big(double2 *a, const double2 *tw, const double2 *B, int Mh, int i,
+                                              Load load, Stash stash, Fetch fetch, Fin fin) {
+  for (int half = 0; half < 2; ++half) {
+    for (int j = threadIdx.x; j < Mh; j += blockDim.x) {
+      double2 v = make_double2(0., 0.);
+      if (j < i) {
+        v = load(j);
+        if (half) v = cmul(v, w_big(j, Mh));
+      }
+      a[j] = v;
+    }
+    __syncthreads();
+    fft_dif(a, tw, Mh);
+    const double2 *Bh = B + (i64)half * Mh;
+    for (int j = threadIdx.x; j < Mh; j += blockDim.x) a[j] = cmul(a[j], Bh[j]);
+    __syncthreads();
+    fft_dit_inv(a, tw, Mh);
+    for (int k = threadIdx.x; k < i; k += blockDim.x) {
+      if (half == 0)
+        stash(k, a[k]);
+      else
+        fin(k, cadd(fetch(k), cmulc(a[k], w_big(k, Mh))));
+    }
+    __syncthreads();
+  }
+}
+
 // forward: one block per (cap ring pair i, component)
 __global__ void cap_fft_fwd_kernel(int ilo, int M, i64 nside, hcu_ptrs maps,
                                    const double2 *bfilt,
@@ -177,6 +251,32 @@ __global__ void cap_fft_fwd_kernel(int ilo, int M, i64 nside, hcu_ptrs maps,
     for (int k = threadIdx.x; k < i; k += blockDim.x)
       Yc[(i64)q * i + k] = cmul(a[k], chirp(k, i));
     __syncthreads();
+  }
+}
+
+// the same for rings whose Bluestein length is 2 Mh (see bluestein_big)
+__global__ void cap_fft_fwd_big_kernel(int ilo, int Mh, i64 nside, hcu_ptrs maps, const double2 *bfilt,
+                                       const i64 *off, double2 *Y, i64 ncap) {
+  extern __shared__ double2 smem[];
+  double2 *a = smem;
+  double2 *tw = smem + Mh;
+  const int i = ilo + blockIdx.x;
+  const int c = blockIdx.y;
+  const i64 npix = 12 * nside * nside;
+  const i64 startN = 2LL * i * (i - 1);
+  const i64 startS = npix - startN - 4LL * i;
+  const double *mN = maps.p[c] + startN;
+  const double *mS = maps.p[c] + startS;
+  const double2 *B = bfilt + off[i];
+  double2 *Yc = Y + (i64)c * ncap + startN;
+  make_twiddles(tw, Mh);
+  __syncthreads();
+  for (int q = 0; q < 4; ++q) {
+    double2 *Yq = Yc + (i64)q * i;
+    bluestein_big(
+        a, tw, B, Mh, i, [&](int j) { return cmul(make_double2(mN[4 * j + q], mS[4 * j + q]), chirp(j, i)); },
+        [&](int k, double2 v) { Yq[k] = v; }, [&](int k) { return Yq[k]; },
+        [&](int k, double2 r) { Yq[k] = cmul(r, chirp(k, i)); });
   }
 }
 
@@ -404,11 +504,67 @@ __global__ void cap_fft_inv_kernel(int ilo, int M, i64 nside, const double2 *Z, 
   }
 }
 
+__global__ void cap_fft_inv_big_kernel(int ilo, int Mh, i64 nside, const double2 *Z, i64 ncap,
+                                       const double2 *bfilt, const i64 *off, hcu_ptrs maps) {
+  extern __shared__ double2 smem[];
+  double2 *a = smem;
+  double2 *tw = smem + Mh;
+  const int i = ilo + blockIdx.x;
+  const int comp = blockIdx.y;
+  const i64 npix = 12 * nside * nside;
+  const i64 startN = 2LL * i * (i - 1);
+  const i64 startS = npix - startN - 4LL * i;
+  double *mN = maps.p[comp] + startN;
+  double *mS = maps.p[comp] + startS;
+  const double2 *Zr = Z + (i64)comp * ncap + startN;
+  const double2 *B = bfilt + off[i];
+  make_twiddles(tw, Mh);
+  __syncthreads();
+  for (int q = 0; q < 4; ++q) {
+    bluestein_big(
+        a, tw, B, Mh, i,
+        [&](int kp) {  // see cap_fft_inv_kernel
+          double2 acc = make_double2(0., 0.);
+          for (int s = 0; s < 4; ++s) {
+            const double2 z = Zr[kp + s * i];
+            const int r = (q * s) & 3;
+            const double2 zr = (r == 0) ? z
+                             : (r == 1) ? make_double2(-z.y, z.x)
+                             : (r == 2) ? make_double2(-z.x, -z.y)
+                                        : make_double2(z.y, -z.x);
+            acc = cadd(acc, zr);
+          }
+          const double2 e = expmipi((double)(q * kp) / (2.0 * (double)i));
+          acc = cmulc(acc, e);
+          return cmul(make_double2(acc.x, -acc.y), chirp(kp, i));
+        },
+        [&](int k, double2 v) { mN[4 * k + q] = v.x; mS[4 * k + q] = v.y; },
+        [&](int k) { return make_double2(mN[4 * k + q], mS[4 * k + q]); },
+        [&](int k, double2 rr) {
+          const double2 r = cmul(rr, chirp(k, i));
+          mN[4 * k + q] = r.x;
+          mS[4 * k + q] = -r.y;
+        });
+  }
+}
+
 int bluestein_M(int i) {
   int need = 2 * i - 1;
   int M = 2;
   while (M < need) M <<= 1;
   return M;
+}
+
+// longest transform one CTA holds in shared memory (24 bytes per point).  HCU_CAP_MAX_M lowers it so that the
+// tests can drive the two-half path of bluestein_big at small nside.
+int cap_max_m() {
+  static int v = 0;
+  if (!v) {
+    const char *e = getenv("HCU_CAP_MAX_M");
+    int x = e ? atoi(e) : 8192;
+    v = (x >= 4 && x <= 8192 && (x & (x - 1)) == 0) ? x : 8192;
+  }
+  return v;
 }
 
 int cap_threads(int M) {
@@ -438,11 +594,19 @@ int hcu_build_bluestein(hcu_ctx *ctx, hcu_geom *g) {
     int M = bluestein_M(i);
     int ihi = i;
     while (ihi + 1 < nside && bluestein_M(ihi + 1) == M) ++ihi;
-    size_t smem = (size_t)M * 24;
-    HCU_CUDA(cudaFuncSetAttribute(bluestein_filter_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bluestein_filter_kernel<<<ihi - i + 1, cap_threads(M), smem, ctx->stream>>>(
-        i, M, g->bfilt, g->bfilt_off);
+    if (M > cap_max_m()) {
+      const int Mh = M / 2;
+      size_t smem = (size_t)Mh * 24;
+      HCU_CUDA(cudaFuncSetAttribute(bluestein_filter_big_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bluestein_filter_big_kernel<<<ihi - i + 1, cap_threads(Mh), smem, ctx->stream>>>(i, Mh, g->bfilt, g->bfilt_off);
+    } else {
+      size_t smem = (size_t)M * 24;
+      HCU_CUDA(cudaFuncSetAttribute(bluestein_filter_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bluestein_filter_kernel<<<ihi - i + 1, cap_threads(M), smem, ctx->stream>>>(
+          i, M, g->bfilt, g->bfilt_off);
+    }
     HCU_LAUNCH_CHECK(ctx);
     i = ihi + 1;
   }
@@ -513,12 +677,21 @@ int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
       int M = bluestein_M(i);
       int ihi = i;
       while (ihi + 1 <= iend && bluestein_M(ihi + 1) == M) ++ihi;
-      size_t smem = (size_t)M * 24;
-      HCU_CUDA(cudaFuncSetAttribute(cap_fft_fwd_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       dim3 grid(ihi - i + 1, ncomp);
-      cap_fft_fwd_kernel<<<grid, cap_threads(M), smem, ctx->stream>>>(
-          i, M, nside, maps, g->bfilt, g->bfilt_off, Y, ncap);
+      if (M > cap_max_m()) {
+        const int Mh = M / 2;
+        size_t smem = (size_t)Mh * 24;
+        HCU_CUDA(cudaFuncSetAttribute(cap_fft_fwd_big_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cap_fft_fwd_big_kernel<<<grid, cap_threads(Mh), smem, ctx->stream>>>(
+            i, Mh, nside, maps, g->bfilt, g->bfilt_off, Y, ncap);
+      } else {
+        size_t smem = (size_t)M * 24;
+        HCU_CUDA(cudaFuncSetAttribute(cap_fft_fwd_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cap_fft_fwd_kernel<<<grid, cap_threads(M), smem, ctx->stream>>>(
+            i, M, nside, maps, g->bfilt, g->bfilt_off, Y, ncap);
+      }
       HCU_LAUNCH_CHECK(ctx);
       i = ihi + 1;
     }
@@ -578,12 +751,21 @@ int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
       int M = bluestein_M(i);
       int ihi = i;
       while (ihi + 1 <= iend && bluestein_M(ihi + 1) == M) ++ihi;
-      size_t smem = (size_t)M * 24;
-      HCU_CUDA(cudaFuncSetAttribute(cap_fft_inv_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       dim3 grid(ihi - i + 1, ncomp);
-      cap_fft_inv_kernel<<<grid, cap_threads(M), smem, ctx->stream>>>(
-          i, M, nside, Z, ncap, g->bfilt, g->bfilt_off, maps);
+      if (M > cap_max_m()) {
+        const int Mh = M / 2;
+        size_t smem = (size_t)Mh * 24;
+        HCU_CUDA(cudaFuncSetAttribute(cap_fft_inv_big_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cap_fft_inv_big_kernel<<<grid, cap_threads(Mh), smem, ctx->stream>>>(
+            i, Mh, nside, Z, ncap, g->bfilt, g->bfilt_off, maps);
+      } else {
+        size_t smem = (size_t)M * 24;
+        HCU_CUDA(cudaFuncSetAttribute(cap_fft_inv_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cap_fft_inv_kernel<<<grid, cap_threads(M), smem, ctx->stream>>>(
+            i, M, nside, Z, ncap, g->bfilt, g->bfilt_off, maps);
+      }
       HCU_LAUNCH_CHECK(ctx);
       i = ihi + 1;
     }

@@ -96,6 +96,22 @@ int hcu_map_values(hcu_ctx *ctx, int64_t nside, int scheme, const double *lon,
                    const double *lat, const double *values,
                    int64_t value_stride, int nv, int64_t n, double *maps,
                    int64_t map_stride, int flags);
+/* One catalogue page -> the position map AND the shear map of a tomographic bin in ONE pass.  The reference's
+ * Positions and Shears fields read the same lon / lat / weight columns of every page
+ * (heracles/fields.py:262-271 and :420-433) and call HealpixMapper.map_values twice; here ang2pix runs once
+ * and five columns instead of seven cross PCIe:
+ *     ipix = ang2pix(lon, lat);  pos[ipix] += w;  she[ipix] += w g1;  she[she_stride + ipix] += w g2
+ * (re, im = w*re, w*im: fields.py:426).  w == NULL: unit weights (fields.py:265,425); pos or she may be NULL.
+ * Rows with w == 0 are left out of the shear map and its sums (page.delete(page[wcol] == 0), fields.py:420-421);
+ * rows with a NaN in a used column are skipped and counted (CatalogPage.get raises on them, catalog/base.py:114-125).
+ * stats: NULL or device / managed float64[8], accumulated (+=) -- the running sums the Field layer keeps per page:
+ *   [0] rows added to pos  [1] sum w  [2] sum w^2              (Positions: ngal, wmean, w2mean, fields.py:269-271)
+ *   [3] rows added to she  [4] sum w  [5] sum w^2  [6] sum w^2 (g1^2 + g2^2)   (Shears: ..., var, fields.py:430-433)
+ *   [7] rows with NaN.
+ * Column pointers are "any" pointers (pageable pages go through the pinned staging slots). */
+int hcu_map_page(hcu_ctx *ctx, int64_t nside, int scheme, const double *lon, const double *lat,
+                 const double *w, const double *g1, const double *g2, int64_t n, double *pos,
+                 double *she, int64_t she_stride, double *stats);
 /* rows skipped since the last call of this function (synchronises) */
 int hcu_bad_rows(hcu_ctx *ctx, int64_t *count);
 
@@ -106,6 +122,9 @@ int hcu_divide(hcu_ctx *ctx, double *x, int64_t n, double a);         /* x /= a 
 int hcu_axpy(hcu_ctx *ctx, double *y, const double *x, double a, int64_t n); /* y += a x */
 int hcu_add_scalar(hcu_ctx *ctx, double *x, int64_t n, double a);     /* x += a        */
 
+/* hp.reorder(map, r2n / n2r): RING <-> NEST order of a whole map (out of place; device or managed memory).
+ * The transform works on RING maps; a mapper configured for NEST maps reorders before hcu_map2alm. */
+int hcu_reorder(hcu_ctx *ctx, int64_t nside, const double *in, double *out, int to_nest);
 /* hp.ud_grade(map, nside_out) -- heracles/healpy.py:205-209 (RING in, RING out, mean preserving) */
 int hcu_ud_grade(hcu_ctx *ctx, int64_t nside_in, const double *in,
                  int64_t nside_out, double *out);
@@ -197,6 +216,8 @@ int hcu_alm2cl_mslice(hcu_ctx *ctx, int na, const void *a, int64_t stride_a,
                       int lmax_out, int m_step, int m_offset, double *cl);
 
 /* ---- introspection --------------------------------------------------------- */
+/* stage timing is off by default (it costs a host wait per Legendre batch); hcu_set_timing(ctx, 1) enables it */
+int hcu_set_timing(hcu_ctx *ctx, int enabled);
 /* device milliseconds of the stages of the last hcu_map2alm / hcu_alm2map call
  * (CUDA events on the context stream): [0] ring FFT stage, [1] Legendre stage,
  * [2] synthesis Legendre, [3] synthesis FFT.  Synchronises. */

@@ -317,3 +317,55 @@ def test_full_map_parity_baseline_configs(hb, name):
                 lmin = spin
                 rel = np.abs(cl[lmin:] - ref_cl[c][lmin:]).max() / np.abs(ref_cl[c][lmin:]).max()
                 assert rel < TOL, (name, spin, int(niter), c, rel)
+
+
+def test_two_half_bluestein_path():
+    """ring numbers i > 4096 (nside 8192) use a Bluestein length 2 x 8192 whose first radix-2 stage runs out of
+    core (k_ringfft.cu: bluestein_big).  HCU_CAP_MAX_M lowers the shared-memory limit so that the SAME code is
+    checked against the oracle at nside 64 (forward and inverse ring FFTs, both spins, iterated)."""
+    import os
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    code = r"""
+import numpy as np, oracle, heracles_b200 as hb
+oracle.build()
+nside, lmax = 64, 128
+rng = np.random.default_rng(3)
+maps = rng.standard_normal((4, 12 * nside * nside))
+for spin in (0, 2):
+    mapper = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=2)
+    a = np.asarray(mapper.transform(maps if spin == 0 else maps.reshape(2, 2, -1), spin=spin)).reshape(4, -1)
+    r = oracle.map2alm(nside, lmax, maps, spin=spin, niter=2)
+    err = np.linalg.norm(a - r) / np.linalg.norm(r)
+    assert err < 1e-10, (spin, err)
+print("ok")
+"""
+    env = dict(os.environ, HCU_CAP_MAX_M="16", PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_sparse_map_nside_8192(hb, oracle):
+    """BASELINE.json config 5 resolution (nside 8192, lmax 16384): sparse-map closed form, spin 0"""
+    nside, lmax = 8192, 16384
+    npix = 12 * nside**2
+    rng = np.random.default_rng(11)
+    # pixels in the small and in the large (i > 4096) polar-cap rings, in the belt, north and south
+    ipix = np.array([3, 2 * 5000 * 4999 + 17, 2 * 8000 * 7999 + 12345, npix // 2 + 5, npix - 2 * 6000 * 6001 + 9, npix - 2])
+    vals = rng.standard_normal(ipix.size)
+    m = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=0)
+    mp = m.create()
+    mp[ipix] = vals
+    alm = np.asarray(m.transform(mp, spin=0))
+    del mp
+    lon, lat = oracle.pix2ang(nside, ipix)
+    theta, phi = np.radians(90.0 - lat), np.radians(lon)
+    w = 4 * np.pi / npix
+    for l, mm in [(0, 0), (2, 1), (5000, 4999), (lmax, 0), (lmax, lmax), (lmax - 1, lmax // 2 - 24), (12345, 6789), (lmax - 3, lmax - 200)]:
+        lam = np.array([oracle.lambda_lm(lmax, mm, 0, np.cos(t), np.sin(t), prec=1)[l] for t in theta])
+        exp = w * np.sum(vals * np.conj(lam * np.exp(1j * mm * phi)))
+        got = alm[mm * (2 * lmax + 1 - mm) // 2 + l]
+        assert abs(got - exp) < 1e-9 * w * np.abs(vals).sum(), (l, mm, got, exp)

@@ -16,6 +16,7 @@ ap.add_argument("--reps", type=int, default=2)
 a = ap.parse_args()
 lmax = a.lmax or 2 * a.nside
 ctx = hb.get_context(0)
+ctx.set_timing(True)
 npix = 12 * a.nside ** 2
 nalm = (lmax + 1) * (lmax + 2) // 2
 maps = torch.randn(a.nmaps, npix, device="cuda", dtype=torch.float64)
