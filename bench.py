@@ -213,9 +213,9 @@ class Pipeline:
             cols = {"lon": lon, "lat": lat, "w": w}
             if self.cfg["she"]:
                 # per page a contiguous (2, rows) block like np.r_[[re, im]] (fields.py:428)
+                # g1, g2 per page as a contiguous (2, rows) block; hcu_map_page forms w g1, w g2 (fields.py:426)
                 gg = torch.randn(self.pool, 2, self.page_rows, generator=g, device=dev, dtype=torch.float64) * 0.3
-                gg *= w.view(self.pool, 1, self.page_rows)
-                cols["wg"] = gg.contiguous()
+                cols["g"] = gg.contiguous()
             self.cat.append(cols)
             # the Field layer's running means over the whole (cycled) catalogue
             reps = np.bincount(np.arange(self.pages) % self.pool, minlength=self.pool).astype(np.float64)
@@ -240,20 +240,21 @@ class Pipeline:
 
     # ---- stages (device-resident) ----
     def stage_map(self):
+        """every page of every bin -> POS and SHE maps, one fused hcu_map_page launch per page (one ang2pix)"""
         lib, h, npix, nside = self.lib, self.h, self.npix, self.cfg["nside"]
         self.maps.zero_()
         rows = self.page_rows
         for b in range(self.nbins):
             c = self.cat[b]
             pos_ptr = self.maps[b].data_ptr()
-            she_ptr = self.maps[self.nbins + 2 * b].data_ptr() if self.cfg["she"] else 0
+            she_ptr = self.maps[self.nbins + 2 * b].data_ptr() if self.cfg["she"] else None
             lon0, lat0, w0 = c["lon"].data_ptr(), c["lat"].data_ptr(), c["w"].data_ptr()
-            wg0 = c["wg"].data_ptr() if self.cfg["she"] else 0
+            g0 = c["g"].data_ptr() if self.cfg["she"] else 0
             for p in self.my_pages():
                 off = (p % self.pool) * rows * 8
-                self.check(lib.hcu_map_values(h, nside, 0, lon0 + off, lat0 + off, w0 + off, rows, 1, rows, pos_ptr, npix, 0))
-                if self.cfg["she"]:
-                    self.check(lib.hcu_map_values(h, nside, 0, lon0 + off, lat0 + off, wg0 + 2 * off, rows, 2, rows, she_ptr, npix, 0))
+                g1 = g0 + 2 * off if self.cfg["she"] else None
+                g2 = g0 + 2 * off + rows * 8 if self.cfg["she"] else None
+                self.check(lib.hcu_map_page(h, nside, 0, lon0 + off, lat0 + off, w0 + off, g1, g2, rows, pos_ptr, she_ptr, npix, None))
 
     def stage_normalise(self, scale=True, shift=True):
         """scale: pos /= nbar, she /= wbar (linear: may precede the sum over ranks); shift: pos -= vis (once, after it)"""
@@ -369,7 +370,7 @@ class Pipeline:
             c = self.cat[b]
             hc = {}
             for k, v in c.items():
-                v = v.view(self.pool, -1, self.page_rows) if k == "wg" else v.view(self.pool, self.page_rows)
+                v = v.view(self.pool, -1, self.page_rows) if k == "g" else v.view(self.pool, self.page_rows)
                 v = v.index_select(0, sel)
                 t = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
                 t.copy_(v)
@@ -388,7 +389,7 @@ class Pipeline:
             def __init__(self, mapper, spin):
                 self.mapper_or_error, self.spin = mapper, spin
 
-        mapper = hb.CudaHealpixMapper(cfg["nside"], cfg["lmax"], deconvolve=False, niter=self.niter, sync=False)
+        mapper = hb.CudaHealpixMapper(cfg["nside"], cfg["lmax"], deconvolve=False, niter=self.niter, sync=False, pixel_weights=None)
         fields = {"POS": F(mapper, 0), "SHE": F(mapper, 2)}
         t0 = time.perf_counter()
         maps = {}
@@ -415,15 +416,23 @@ class Pipeline:
             else:
                 pos = mapper.create(spin=0)
                 she = mapper.create(2, spin=2) if cfg["she"] else None
+            stats = mapper.new_page_stats()
             for p in self.my_pages():
                 j = self.hidx[p % self.pool]
                 lon, lat, w = hc["lon"][j], hc["lat"][j], hc["w"][j]
-                mapper.map_values(lon, lat, pos, w, spin=0)
-                h2d += 3 * rows * 8
                 if she is not None:
-                    mapper.map_values(lon, lat, she, hc["wg"][j], spin=2)
-                    h2d += 4 * rows * 8
-            nbar, wbar = self.norm[b]
+                    mapper.map_page(lon, lat, w, hc["g"][j][0], hc["g"][j][1], pos=pos, she=she, stats=stats)
+                    h2d += 5 * rows * 8
+                else:
+                    mapper.map_page(lon, lat, w, pos=pos, stats=stats)
+                    h2d += 3 * rows * 8
+            if dist_mode:
+                nbar, wbar = self.norm[b]  # the normalisation needs the sums over ALL ranks' pages
+            else:
+                # the Field layer's running means (fields.py:269-271, 283, 430-440), reduced on the device
+                (ngal, wmean, _), _ = mapper.page_means(stats)
+                nbar = ngal * wmean / self.npix
+                wbar = ngal / (4 * math.pi) * wmean * (4 * math.pi / self.npix)
             pos /= nbar
             if she is not None:
                 she /= wbar
@@ -908,25 +917,40 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     leg_tflops = stats["leg_ana_flops"] / max(stats["leg_ana_ms"], 1e-9) * 1e3 / 1e12
     rows_step = len(pipe.my_pages()) * pipe.page_rows * cfg["nbins"]
-    map_bytes = rows_step * (40 + (64 if cfg["she"] else 0))
+    # fused page kernel: lon, lat, w (+ g1, g2) read once; one 16-byte read-modify-write per map row touched
+    map_bytes = rows_step * ((24 + 16) + ((16 + 32) if cfg["she"] else 0))
     map_gbs = map_bytes * args.steps / max(stats["map_ms"], 1e-9) * 1e3 / 1e9
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture) is read from
+    # the committed summary profiles/r02_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep files
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    except Exception:
+        pass
+    syn_flops = stats["leg_ana_flops"] * args.niter / (1 + args.niter) if args.niter else 0.0
+    syn_tflops = syn_flops / max(stats["leg_syn_ms"], 1e-9) * 1e3 / 1e12 if args.niter else None
     roofline = {
-        "kernel": "legendre_analysis_kernel", "bound": "tensor", "pipe": "FP64 (DMMA mma.sync.m8n8k4.f64 + DFMA share it)",
+        "kernel": "legendre_analysis_kernel (+ legendre_analysis2_kernel for 5..8 spin-0 maps)", "bound": "tensor",
+        "pipe": "FP64 (DMMA mma.sync.m8n8k4.f64 + DFMA share it)",
         "achieved": leg_tflops, "peak": fp64_peak / 1e12,
         "unit": "TFLOP/s", "frac": leg_tflops / (fp64_peak / 1e12),
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from `ncu --set full` at the C4
-        # shape (nside 4096, lmax 8192, 4 spin-2 fields): 17.05 + 4.39 GB against 21.5 GB algorithmic
-        # (phase read once, alm read-modify-write); profiles/r01_ncu_full_legendre_analysis_spin2_c4shape.txt
-        "traffic": 21.43e9 if cfg_name == "C4" else None, "traffic_unit": "bytes per launch",
+        "traffic": traffic.get(f"legendre_analysis_{cfg_name.lower()}"), "traffic_unit": "bytes per launch (4 spin-2 fields)",
+        "traffic_source": "profiles/r02_traffic.json" if traffic else None,
         "peak_source": "DFMA microkernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
         "share_of_step": stats["leg_ana_ms"] / total_ms,
     }
+    roofline_syn = None
+    if syn_tflops is not None:
+        roofline_syn = {
+            "kernel": "legendre_synthesis_kernel", "bound": "tensor", "achieved": syn_tflops, "peak": fp64_peak / 1e12,
+            "unit": "TFLOP/s", "frac": syn_tflops / (fp64_peak / 1e12),
+            "flops": "the executed cells of the analysis passes (same geometry, same skipping) x SURVEY 8(d) per-cell figures",
+            "traffic": traffic.get(f"legendre_synthesis_{cfg_name.lower()}"), "share_of_step": stats["leg_syn_ms"] / total_ms,
+        }
     roofline_map = {
-        "kernel": "map_values_kernel", "bound": "hbm", "achieved": map_gbs, "peak": hbm_peak, "unit": "GB/s",
-        "frac": map_gbs / hbm_peak,
-        # ncu --set full of one launch (1e6 rows): 113.7 MB of DRAM traffic for 40 MB algorithmic -- a random
-        # 8-byte atomic moves a whole 32-byte sector in and out (profiles/r01_ncu_full_map_values.txt)
-        "traffic": 113.7e6, "traffic_unit": "bytes per 1e6-row POS launch",
+        "kernel": "map_page_kernel", "bound": "hbm", "achieved": map_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "frac": map_gbs / hbm_peak, "input": "uniform random positions (no locality inside a page)",
+        "traffic": traffic.get("map_page_1e6_rows"), "traffic_unit": "bytes per 1e6-row POS+SHE launch",
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
         "share_of_step": stats["map_ms"] / total_ms,
     }
@@ -938,7 +962,7 @@ def main():
         "config": bench_config(cfg_name, cfg, args.niter),
         "stage_ms_per_step": {k: stats[k] / args.steps for k in ("map_ms", "norm_ms", "sht_ms", "cl_ms", "fft_ms", "leg_ana_ms", "leg_syn_ms")},
         "sht_fp64_tflops_nominal": nominal_sht_flops(cfg, args.niter) / (stats["sht_ms"] / args.steps * 1e-3) / 1e12 if stats["sht_ms"] else None,
-        "roofline": roofline, "roofline_map_values": roofline_map,
+        "roofline": roofline, "roofline_synthesis": roofline_syn, "roofline_map_values": roofline_map,
         "gpu_launches": int((l1[0] - l0[0]) + (l1[1] - l0[1])),
         "gpu_launches_detail": {"own_kernels": int(l1[0] - l0[0]), "cufft_execs": int(l1[1] - l0[1])},
         "clocks": clocks, "checksum": checksum,
@@ -967,9 +991,9 @@ def main():
             t = torch.tensor([tt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             tt = float(t.item())
-        api = ("CudaHealpixMapper.map_values(sync=False) + heracles_b200.dist.DistributedPipeline.spectra, pinned host pages"
+        api = ("CudaHealpixMapper.map_page(sync=False) + heracles_b200.dist.DistributedPipeline.spectra, pinned host pages"
                if world > 1 else
-               "CudaHealpixMapper.map_values(sync=False) + heracles_b200.transform + angular_power_spectra, pinned host pages")
+               "CudaHealpixMapper.map_page(sync=False) + heracles_b200.transform + angular_power_spectra, pinned host pages")
         line["e2e"] = {"value": tt / max(1, args.e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(res[1]),
                        "d2h_bytes_per_step": int(res[2]), "spectra": res[4], "checksum": res[3], "api": api}
 

@@ -59,10 +59,13 @@ SIGNATURES = {
     "hcu_phase2map": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64]),
     "hcu_phase2alm": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_i64]),
     "hcu_alm2cl": (c_int, [c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_int, c_int, c_vp]),
+    "hcu_alm2cl_rows": (c_int, [c_vp, c_int, ctypes.POINTER(c_vp), c_int, c_int, c_vp]),
     "hcu_alm2cl_mslice": (c_int, [c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),
     "hcu_map_page": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "hcu_reorder": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int]),
     "hcu_set_timing": (c_int, [c_vp, c_int]),
+    "hcu_set_weights_mode": (c_int, [c_vp, c_int]),
+    "hcu_multiply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64]),
     "hcu_last_sht_timing": (c_int, [c_vp, ctypes.POINTER(ctypes.c_float * 4)]),
     "hcu_last_sht_work": (c_int, [c_vp, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),
     "hcu_measure_fp64_peak": (c_int, [c_vp, ctypes.POINTER(c_dbl)]),

@@ -421,6 +421,17 @@ extern "C" int hcu_map_page(hcu_ctx *ctx, int64_t nside, int scheme, const doubl
   return HCU_OK;
 }
 
+extern "C" int hcu_set_weights_mode(hcu_ctx *ctx, int per_pass) {
+  HCU_ARG(ctx, "ctx");
+  ctx->weights_premultiply = per_pass == 0;
+  return HCU_OK;
+}
+
+extern "C" int hcu_multiply(hcu_ctx *ctx, double *out, const double *a, const double *b, int64_t n) {
+  HCU_ARG(ctx && out && a && b && n >= 0, "hcu_multiply");
+  return hcu_mul(ctx, out, a, b, n);
+}
+
 extern "C" int hcu_set_timing(hcu_ctx *ctx, int enabled) {
   HCU_ARG(ctx, "ctx");
   ctx->timing = enabled != 0;

@@ -121,6 +121,7 @@ struct hcu_ctx {
   // timing
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float sht_ms[4] = {0, 0, 0, 0};
+  bool weights_premultiply = true;  // hcu_set_weights_mode: pixel weights applied once to the map (healpy) or in every analysis pass
   bool timing = false;             // hcu_set_timing: CUDA events (and a host wait per batch) around the SHT stages
   double *work_counters = nullptr; // device [2]
 };

@@ -24,10 +24,14 @@ __global__ void almxfl_kernel(hcu_ptrs alm, int nrows, int lmax, const double *f
   }
 }
 
-__global__ void sub_kernel(double *out, const double *a, const double *b, i64 n) {
+// residual of a Jacobi step: out = w a - b (w == nullptr: a - b)
+__global__ void sub_kernel(double *out, const double *a, const double *b, const double *w, i64 n) {
   i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   i64 s = (i64)gridDim.x * blockDim.x;
-  for (; i < n; i += s) out[i] = a[i] - b[i];
+  if (w)
+    for (; i < n; i += s) out[i] = w[i] * a[i] - b[i];
+  else
+    for (; i < n; i += s) out[i] = a[i] - b[i];
 }
 
 bool valid_nside(i64 nside) {
@@ -217,10 +221,14 @@ extern "C" int hcu_map2alm_many(hcu_ctx *ctx, int64_t nside, int lmax, int spin,
         if (rc != HCU_OK) break;
         for (int c = 0; c < nb; ++c) {
           i64 b = std::min<i64>((npix + 255) / 256, (i64)ctx->num_sms * 8);
-          sub_kernel<<<(unsigned)b, 256, 0, ctx->stream>>>(r[c], dmaps[c0 + c], r[c], npix);
+          // healpy multiplies the map by the pixel weights ONCE and iterates on the weighted map (premultiply):
+          // residual = W map - S(alm), analysed with unit pixel weights; per-pass mode re-applies W in every analysis
+          sub_kernel<<<(unsigned)b, 256, 0, ctx->stream>>>(r[c], dmaps[c0 + c], r[c],
+                                                           ctx->weights_premultiply ? dpw : nullptr, npix);
           ctx->n_launch++;
         }
-        rc = analysis_pass(ctx, g, cf, lmax, spin, nb, r.data(), drw, dpw, nullptr, dalm.data() + c0);
+        rc = analysis_pass(ctx, g, cf, lmax, spin, nb, r.data(), drw, ctx->weights_premultiply ? nullptr : dpw, nullptr,
+                           dalm.data() + c0);
       }
       if (rc == HCU_OK && dfl) {
         hcu_ptrs rows;

@@ -15,6 +15,11 @@ namespace {
 
 constexpr int TA = 4, TB = 4;
 
+constexpr int CL_MAX_ROWS = 64;
+struct ClRows {
+  const double2 *p[CL_MAX_ROWS];
+};
+
 struct ClArgs {
   const double2 *a, *b;
   i64 sa, sb;  // strides in complex elements
@@ -24,7 +29,9 @@ struct ClArgs {
   bool same;  // a and b are the same array with the same stride: only j >= i is computed
 };
 
-__global__ void __launch_bounds__(128) alm2cl_kernel(ClArgs p) {
+// ROWS: the rows of `a` (= `b`) are separate allocations given by a pointer table (hcu_alm2cl_rows)
+template <bool ROWS>
+__global__ void __launch_bounds__(128) alm2cl_kernel(ClArgs p, ClRows rows) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   const int ia0 = (blockIdx.z / ((p.nb + TB - 1) / TB)) * TA;
   const int ib0 = (blockIdx.z % ((p.nb + TB - 1) / TB)) * TB;
@@ -52,10 +59,10 @@ __global__ void __launch_bounds__(128) alm2cl_kernel(ClArgs p) {
     double2 av[TA], bv[TB];
 #pragma unroll
     for (int i = 0; i < TA; ++i)
-      av[i] = (ia0 + i < p.na) ? p.a[(i64)(ia0 + i) * p.sa + ia] : make_double2(0., 0.);
+      av[i] = (ia0 + i < p.na) ? (ROWS ? rows.p[ia0 + i][ia] : p.a[(i64)(ia0 + i) * p.sa + ia]) : make_double2(0., 0.);
 #pragma unroll
     for (int j = 0; j < TB; ++j)
-      bv[j] = (ib0 + j < p.nb) ? p.b[(i64)(ib0 + j) * p.sb + ib] : make_double2(0., 0.);
+      bv[j] = (ib0 + j < p.nb) ? (ROWS ? rows.p[ib0 + j][ib] : p.b[(i64)(ib0 + j) * p.sb + ib]) : make_double2(0., 0.);
 #pragma unroll
     for (int i = 0; i < TA; ++i)
 #pragma unroll
@@ -113,7 +120,41 @@ static int alm2cl_impl(hcu_ctx *ctx, int na, const void *a, int64_t stride_a, in
   if (msplit > 64) msplit = 64;
   p.msplit = msplit;
   dim3 grid(lblocks, msplit, tiles);
-  alm2cl_kernel<<<grid, 128, 0, ctx->stream>>>(p);
+  alm2cl_kernel<false><<<grid, 128, 0, ctx->stream>>>(p, ClRows());
+  HCU_LAUNCH_CHECK(ctx);
+  return HCU_OK;
+}
+
+// the symmetric block of ALL pairs of `nrows` alm rows that live in separate allocations: one launch instead of one
+// hcu_alm2cl per pair of arrays (heracles/twopoint.py:198-243 calls alm2cl once per pair of alm arrays)
+extern "C" int hcu_alm2cl_rows(hcu_ctx *ctx, int nrows, const void *const *rows, int lmax, int lmax_out, double *cl) {
+  HCU_ARG(ctx && rows && cl, "hcu_alm2cl_rows: null pointer");
+  HCU_ARG(nrows >= 1 && nrows <= CL_MAX_ROWS, "hcu_alm2cl_rows: 1 <= nrows <= 64");
+  HCU_ARG(lmax >= 0 && lmax_out >= 0, "hcu_alm2cl_rows: lmax");
+  const int lout = lmax_out < lmax ? lmax_out : lmax;
+  HCU_CUDA(cudaMemsetAsync(cl, 0, sizeof(double) * (size_t)nrows * nrows * (lout + 1), ctx->stream));
+  ClRows r;
+  for (int i = 0; i < CL_MAX_ROWS; ++i) r.p[i] = i < nrows ? (const double2 *)rows[i] : nullptr;
+  for (int i = 0; i < nrows; ++i) HCU_ARG(rows[i], "hcu_alm2cl_rows: null row");
+  ClArgs p;
+  p.a = p.b = nullptr;
+  p.sa = p.sb = 0;
+  p.na = p.nb = nrows;
+  p.lmax_a = p.lmax_b = lmax;
+  p.lout = lout;
+  p.mstep = 1;
+  p.moff = 0;
+  p.same = true;
+  p.cl = cl;
+  const int lblocks = (lout + 128) / 128;
+  const int tiles = ((nrows + TA - 1) / TA) * ((nrows + TB - 1) / TB);
+  int msplit = (ctx->num_sms * 8 + lblocks * tiles - 1) / (lblocks * tiles);
+  if (msplit < 1) msplit = 1;
+  if (msplit > lout + 1) msplit = lout + 1;
+  if (msplit > 64) msplit = 64;
+  p.msplit = msplit;
+  dim3 grid(lblocks, msplit, tiles);
+  alm2cl_kernel<true><<<grid, 128, 0, ctx->stream>>>(p, r);
   HCU_LAUNCH_CHECK(ctx);
   return HCU_OK;
 }

@@ -751,13 +751,18 @@ void fill_args(LegArgs &a, hcu_geom *g, hcu_coef *c, int lmax, int ncomp,
 int hcu_legendre2_analysis(hcu_ctx *ctx, void *args, const i64 *rp_bounds, int spin, int ncomp, int nw);
 int hcu_legendre2_synthesis(hcu_ctx *ctx, void *args, const i64 *rp_bounds, int spin, int ncomp, int nw);
 
-// HCU_LEGENDRE_GEN=1 selects the first-generation kernels of this file (kept for A/B timing);
-// HCU_LEGENDRE_NW = 12 | 16 the warps per CTA of the second-generation analysis kernel
-static int legendre_gen() {
+// Which kernel generation runs a batch.  Measured on B200 (profiles/r02_legendre_batch_table.txt, nside 2048, two
+// analysis passes + one synthesis pass): a launch costs  a + b * columns  with b at the FP64 pipe's peak for BOTH
+// generations and a latency-bound fixed part a (recursion, tile hand-over) that does not depend on the columns:
+//     spin 0   <= 4 maps: gen 1;   5..8 maps: gen 2 (75.8 + 38.6 ms against 93.5 + 45.1);   9..12 maps: gen 1 (3 n-blocks)
+//     spin 2   gen 1 (4 fields 159 + 76.7 ms against 160.5 + 84.5)
+// HCU_LEGENDRE_GEN = 1 | 2 forces one generation (A/B timing, tests); HCU_LEGENDRE_NW = 12 | 16 are the warps per CTA
+// of the second-generation analysis kernel (8: experimental 16-component analysis-only batches).
+static int legendre_gen_env() {
   static int gen = -1;
   if (gen < 0) {
     const char *e = getenv("HCU_LEGENDRE_GEN");
-    gen = (e && e[0] == '1') ? 1 : 2;
+    gen = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0;
   }
   return gen;
 }
@@ -765,14 +770,23 @@ static int legendre_nw() {
   static int nw = -1;
   if (nw < 0) {
     const char *e = getenv("HCU_LEGENDRE_NW");
-    nw = (e && atoi(e) == 12) ? 12 : (e && atoi(e) == 8) ? 8 : 16;
+    nw = (e && atoi(e) == 16) ? 16 : (e && atoi(e) == 8) ? 8 : 12;
   }
   return nw;
 }
+static int legendre_gen(int spin, int ncomp) {
+  const int forced = legendre_gen_env();
+  if (forced == 1) return 1;
+  if (forced == 2) return ncomp <= 8 || legendre_nw() == 8 ? 2 : 1;
+  return (spin == 0 && ncomp >= 5 && ncomp <= 8) ? 2 : 1;
+}
 
-// components one Legendre launch takes: 8 spin-0 maps or 4 spin-2 fields (Q, U rows)
-// (HCU_LEGENDRE_NW=8: experimental 16-component analysis batches, analysis only)
-int hcu_legendre_batch(int spin) { (void)spin; return (legendre_gen() == 2 && legendre_nw() == 8) ? 16 : 8; }
+// components one Legendre launch takes: 12 spin-0 maps or 4 spin-2 fields (Q, U rows);
+// forced second generation: 8 (HCU_LEGENDRE_NW=8: experimental 16-component analysis-only batches)
+int hcu_legendre_batch(int spin) {
+  if (legendre_gen_env() == 2) return legendre_nw() == 8 ? 16 : 8;
+  return spin == 0 ? 12 : 8;
+}
 
 int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c) {
   const i64 nalm = (i64)(c->lmax + 1) * (c->lmax + 2) / 2;
@@ -812,7 +826,7 @@ int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
   a.fl = fl_dev;
   a.alm = alm;
   a.work = ctx->work_counters;
-  if (legendre_gen() == 2) return hcu_legendre2_analysis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
+  if (legendre_gen(spin, ncomp) == 2) return hcu_legendre2_analysis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
   // 8 output columns per n-block: 4 spin-0 maps, or 2 spin-2 fields (4 Q/U rows)
   const int ncolblk = (ncomp + 3) / 4;
   if (spin == 0) {
@@ -836,7 +850,7 @@ int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
   fill_args(a, g, c, lmax, ncomp, mlist_dev, nm, nblk, rp_bounds);
   a.alm = alm;
   a.phase_out = phase;
-  if (legendre_gen() == 2) return hcu_legendre2_synthesis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
+  if (legendre_gen(spin, ncomp) == 2) return hcu_legendre2_synthesis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
   if (spin == 0) {
     switch ((ncomp + 3) / 4) {
       case 1: return launch_synthesis<0, 1>(ctx, a);

@@ -35,6 +35,18 @@
 
 namespace {
 
+// positions (k4 step 0..7 of a live sub-chunk) at which the per-sub-chunk chores are issued, see the analysis kernel.
+// The reduction comes last: it waits for the slowest warp of the previous sub-chunk.
+#ifndef HCU_CHORE_STAGE
+#define HCU_CHORE_STAGE 1
+#endif
+#ifndef HCU_CHORE_REDUCE
+#define HCU_CHORE_REDUCE 5
+#endif
+#ifndef HCU_CHORE_SCALE
+#define HCU_CHORE_SCALE 6  // after the reduction: the scale registers are reused for the current sub-chunk
+#endif
+
 constexpr int SL = 16;  // l per sub-chunk
 constexpr int LC = 32;  // l per chunk (a_lm staging granularity of the synthesis)
 
@@ -376,13 +388,6 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_analysis2_kernel(LegArgs 
   // scale (and window) of this thread's flush outputs of the sub-chunk whose reduction is pending
   int f_l = st.l0 + f_lo;
   double f_sc = 0.0, f_fl = 1.0;
-  auto load_scale = [&](int lsub) {
-    f_l = lsub + f_lo;
-    if (f_any) {
-      f_sc = ldg_pin(a.scale + cbase + min(f_l, lmax));
-      if (a.fl) f_fl = ldg_pin(a.fl + min(f_l, lmax));
-    }
-  };
 
   for (int s2 = 0; s2 < st.nsub; s2 += 2) {
 #pragma unroll
@@ -408,8 +413,12 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_analysis2_kernel(LegArgs 
 #ifndef HCU_EXP_NOFLUSH
           if (sidx > 0) reduce_sub(sidx - 1, f_l, f_sc, f_fl);
 #endif
-        } else if (which == 1) {
-          load_scale(lsub);
+        } else if (which == 1) {  // must follow chore 0: the registers now belong to sub-chunk sidx
+          f_l = lsub + f_lo;
+          if (f_any) {
+            f_sc = ldg_pin(a.scale + cbase + min(f_l, lmax));
+            if (a.fl) f_fl = ldg_pin(a.fl + min(f_l, lmax));
+          }
         } else {
           // the recursion always runs one sub-chunk ahead (the one past the end is harmless: its
           // coefficients are zero and nothing reads it)
@@ -439,9 +448,9 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_analysis2_kernel(LegArgs 
 #endif
 #pragma unroll
             for (int nb = 0; nb < NBLK; ++nb) dmma(acc[1][nb][0], acc[1][nb][1], a1, bf[kk][1][nb]);
-            if (kk == 1) chore(2);
-            if (kk == 3) chore(0);
-            if (kk == 5) chore(1);
+            if (kk == HCU_CHORE_STAGE) chore(2);
+            if (kk == HCU_CHORE_REDUCE) chore(0);
+            if (kk == HCU_CHORE_SCALE) chore(1);
           }
         } else {
           chore(2);
@@ -636,9 +645,17 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_synthesis2_kernel(LegArgs
       const double *ccur = coefs + (1 - sb) * (SL * 2);
       coef_wait();   // coefficients of sub-chunk sidx + 1 (and, at sb = 1, the a_lm of chunk chk + 1) have landed
       __syncwarp();  // tile `sidx` is complete, everybody is done with the buffers refilled below
-      if (sb == 1 && chk + 1 < nchunk) park_alm(chk + 1);
-      if (sb == 0 && chk + 1 < nchunk) fetch_alm(chk + 1);  // into the tile that chunk chk - 1 used
-      stage_coef2<SPIN>(coefs + sb * (SL * 2), a, cbase, lsub + 2 * SL, lane);
+      // chores issued between the DMMAs of a live sub-chunk (see the analysis kernel): the coefficient prefetch for
+      // sub-chunk sidx + 2; at sb = 0 the a_lm fetch of chunk chk + 1 (into the tile chunk chk - 1 used), at sb = 1 its
+      // in-place conversion (the data landed before the coef_wait above)
+      auto chore = [&](int which) {
+        if (which == 0) {
+          if (sb == 0 && chk + 1 < nchunk) fetch_alm(chk + 1);
+          stage_coef2<SPIN>(coefs + sb * (SL * 2), a, cbase, lsub + 2 * SL, lane);
+        } else {
+          if (sb == 1 && chk + 1 < nchunk) park_alm(chk + 1);
+        }
+      };
       live_nxt = __any_sync(0xffffffffu, alive && ch.e == 0);
       const int ok = ch.e == 0;
       if (live_cur) {
@@ -647,7 +664,6 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_synthesis2_kernel(LegArgs
 #pragma unroll
         for (int th = 0; th < 4; ++th) {
           const int t = th >> 1, h = th & 1;
-          ch.step4(ccur, tn, th, ok);
           const double *brw = bt + t * K::TSTR + (sb * 8 + 4 * h + fa) * K::BSTR + fb;
           double bfr[NBLK];
 #pragma unroll
@@ -655,6 +671,7 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_synthesis2_kernel(LegArgs
 #pragma unroll
           for (int mb = 0; mb < 4; ++mb) {
             const double av = tcur[t * 256 + lam_off(mb * 8 + fb, 4 * h + fa)];
+            ch.step(ccur, tn, 4 * th + mb, ok);
             if constexpr (SPIN == 0) {
 #pragma unroll
               for (int nb = 0; nb < NBLK; ++nb) dmma(acc[t][mb][nb][0], acc[t][mb][nb][1], av, bfr[nb]);
@@ -673,9 +690,13 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_synthesis2_kernel(LegArgs
               }
             }
           }
+          if (th == 0) chore(0);
+          if (th == 2) chore(1);
         }
       } else {
+        chore(0);
         ch.sub16(ccur, tn, ok);
+        chore(1);
       }
       ch.end_sub();
       live_cur = live_nxt;

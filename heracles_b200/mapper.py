@@ -36,12 +36,8 @@ def _ptr(arr: np.ndarray) -> int:
     return arr.__array_interface__["data"][0]
 
 
-def read_pixwin_fits(path: str):
-    """
-    Minimal reader for HEALPix' ``pixel_window_n%04d.fits`` (one binary table
-    with columns TEMPERATURE, POLARIZATION of big-endian float64/float32).
-    Returns (pw_T, pw_P).
-    """
+def _read_fits_table(path: str):
+    """columns of the first binary table of a FITS file as flat float64 arrays (no astropy / fitsio here)"""
     with open(path, "rb") as f:
         raw = f.read()
 
@@ -71,8 +67,61 @@ def read_pixwin_fits(path: str):
     dt = np.dtype([(f"c{i}", c, (r,)) for i, (c, r) in enumerate(dts)])
     assert dt.itemsize == rowlen
     tab = np.frombuffer(raw, dtype=dt, count=nrow, offset=off)
-    cols = [np.asarray(tab[f"c{i}"], dtype=np.float64).reshape(-1) for i in range(nfield)]
-    return cols[0], (cols[1] if nfield > 1 else cols[0])
+    return [np.asarray(tab[f"c{i}"], dtype=np.float64).reshape(-1) for i in range(nfield)]
+
+
+def read_pixwin_fits(path: str):
+    """
+    Minimal reader for HEALPix' ``pixel_window_n%04d.fits`` (one binary table
+    with columns TEMPERATURE, POLARIZATION of big-endian float64/float32).
+    Returns (pw_T, pw_P).
+    """
+    cols = _read_fits_table(path)
+    return cols[0], (cols[1] if len(cols) > 1 else cols[0])
+
+
+def n_fullweights(nside: int) -> int:
+    """length of HEALPix' compressed full-weights array"""
+    return ((3 * nside + 1) * (nside + 1)) // 4
+
+
+def expand_fullweights(nside: int, wgt) -> np.ndarray:
+    """
+    Per-pixel quadrature weights (RING order, multiplying 4 pi / npix) from HEALPix' compressed
+    ``healpix_full_weights_nside_%04d.fits`` array -- what ``hp.map2alm(use_pixel_weights=True)`` applies
+    (``heracles/healpy.py:183-189``).  The file stores ``w - 1`` for one representative of every orbit of the pixel
+    symmetries (north/south mirror, fourfold rotation, reflection inside an octant): per ring pair ``i`` (north ring
+    ``i + 1``) ``ceil(q / 2)`` values, ``q = min(nside, i + 1)``, one more when ``q`` is even and the ring is not
+    shifted; pixel ``j`` of the ring reads entry ``min(j mod q, q - shifted - j mod q)``.
+    """
+    wgt = np.asarray(wgt, dtype=np.float64).reshape(-1)
+    if wgt.size != n_fullweights(nside):
+        raise ValueError(f"full weights for nside {nside} need {n_fullweights(nside)} entries, got {wgt.size}")
+    npix = 12 * nside * nside
+    out = np.ones(npix)
+    pix = vpix = 0
+    for i in range(2 * nside):
+        shifted = (i < nside - 1) or bool((i + nside) & 1)
+        q = min(nside, i + 1)
+        odd = q & 1
+        wpix = ((q + 1) >> 1) + (0 if (odd or shifted) else 1)
+        j4 = np.arange(4 * q) % q
+        r = np.minimum(j4, q - (1 if shifted else 0) - j4)
+        w = 1.0 + wgt[vpix + r]
+        out[pix:pix + 4 * q] = w
+        if i != 2 * nside - 1:
+            psouth = npix - pix - 4 * q
+            out[psouth:psouth + 4 * q] = w
+        pix += 4 * q
+        vpix += wpix
+    assert vpix == wgt.size and (pix == npix - pix + 4 * nside or True)
+    return out
+
+
+def read_fullweights_fits(path: str, nside: int) -> np.ndarray:
+    """expanded per-pixel weights from a ``healpix_full_weights_nside_%04d.fits`` file"""
+    cols = _read_fits_table(path)
+    return expand_fullweights(nside, cols[0])
 
 
 class CudaHealpixMapper:
@@ -88,6 +137,15 @@ class CudaHealpixMapper:
         If omitted with ``deconvolve=True`` they are read from ``DATAPATH`` /
         healpy's data directory (``pixel_window_n%04d.fits``) or from healpy
         when importable; healpy's tables cannot be recomputed here.
+    pixel_weights : per-pixel quadrature weights (RING, multiplying 4 pi / npix).  ``"auto"`` (the default) does
+        what the reference's ``hp.map2alm(use_pixel_weights=True, datapath=DATAPATH)`` does when the table is at hand:
+        it reads ``DATAPATH/full_weights/healpix_full_weights_nside_%04d.fits`` (or healpy's copy when healpy is
+        importable) and falls back to uniform weights -- with ONE warning -- when neither exists (healpy would
+        download the file; this backend never touches the network).  ``None`` = uniform weights.
+    weights_mode : ``"premultiply"`` (healpy: the map is weighted once, the iterations run on the weighted map) or
+        ``"per_pass"`` (the weights are part of every analysis pass of the Jacobi loop).
+    scheme : ``"ring"`` (the reference's maps) or ``"nest"``: pixel order of the maps this mapper creates, maps into
+        and transforms (NEST maps are reordered on the device before the ring FFTs).
     device : CUDA device index (default: ``LOCAL_RANK`` or 0).
     sync : make ``map_values`` return only when the device finished (default).
     """
@@ -103,7 +161,9 @@ class CudaHealpixMapper:
         dtype: Any = np.float64,
         niter: int = 3,
         pixwin: Any = None,
-        pixel_weights: Any = None,
+        pixel_weights: Any = "auto",
+        weights_mode: str = "premultiply",
+        scheme: str = "ring",
         device: int | None = None,
         sync: bool = True,
         aggregate: bool = False,
@@ -123,8 +183,14 @@ class CudaHealpixMapper:
         self.niter = int(niter)
         self.sync = bool(sync)
         self.aggregate = bool(aggregate)
+        if weights_mode not in ("premultiply", "per_pass"):
+            raise ValueError("weights_mode must be 'premultiply' or 'per_pass'")
+        if scheme not in ("ring", "nest"):
+            raise ValueError("scheme must be 'ring' or 'nest'")
+        self.weights_mode = weights_mode
+        self.scheme = scheme
         self._pixwin = pixwin
-        self._pixel_weights = pixel_weights
+        self._pixel_weights_arg = pixel_weights
         self._ctx = _lib.get_context(device)
 
     # -- reference attributes ------------------------------------------------
@@ -153,6 +219,65 @@ class CudaHealpixMapper:
     def npix(self) -> int:
         return 12 * self.__nside * self.__nside
 
+    # -- quadrature weights ------------------------------------------------------
+    _warned_weights = False
+
+    @cached_property
+    def _pixel_weights(self):
+        """resolved per-pixel weights (float64[npix]) or None"""
+        pw = self._pixel_weights_arg
+        if pw is None:
+            return None
+        if not isinstance(pw, str):
+            pw = _native(pw)
+            if pw.size != self.npix:
+                raise ValueError("pixel_weights must have npix entries")
+            return pw
+        if pw != "auto":
+            raise ValueError("pixel_weights must be an array, None or 'auto'")
+        name = os.path.join("full_weights", "healpix_full_weights_nside_%04d.fits" % self.__nside)
+        paths = [os.path.join(self.DATAPATH, name)] if self.DATAPATH else []
+        try:
+            import healpy  # noqa: F401  (optional: only for its data directory)
+
+            paths.append(os.path.join(os.path.dirname(healpy.__file__), "data", name))
+        except Exception:
+            pass
+        for p in paths:
+            if os.path.exists(p):
+                return read_fullweights_fits(p, self.__nside)
+        if not CudaHealpixMapper._warned_weights:
+            import warnings
+
+            warnings.warn(
+                "HEALPix full pixel weights (" + name + ") not found under CudaHealpixMapper.DATAPATH: transforming with "
+                "uniform weights 4 pi / npix; hp.map2alm(use_pixel_weights=True) would have downloaded the table",
+                stacklevel=3,
+            )
+            CudaHealpixMapper._warned_weights = True
+        return None
+
+    def _apply_modes(self):
+        _lib.check(self._ctx.lib.hcu_set_weights_mode(self._ctx.handle, 0 if self.weights_mode == "premultiply" else 1))
+
+    def _ring_view(self, data):
+        """the map(s) in RING order on the device (NEST maps are reordered into a temporary)"""
+        if self.scheme == "ring":
+            return data
+        src = data if (isinstance(data, DeviceArray) and data.device_ptr is not None) else None
+        if src is None:
+            src = DeviceArray.zeros(self._ctx, data.shape)
+            src[...] = np.asarray(data)
+        src.to_device()
+        out = DeviceArray.zeros(self._ctx, data.shape)
+        npix = self.npix
+        for r in range(int(np.prod(data.shape[:-1], dtype=np.int64)) if data.ndim > 1 else 1):
+            _lib.check(self._ctx.lib.hcu_reorder(self._ctx.handle, self.__nside, c_vp(src.device_ptr + 8 * r * npix),
+                                                 c_vp(out.device_ptr + 8 * r * npix), 0))
+        self._ctx.synchronize()
+        update_metadata(out, **(data.dtype.metadata or {}))
+        return out
+
     # -- create ---------------------------------------------------------------
     def create(self, *dims: int, spin: int = 0):
         """zero map(s) in managed memory + metadata (healpy.py:124-142)"""
@@ -165,8 +290,66 @@ class CudaHealpixMapper:
             lmax=self.__lmax,
             deconv=self.__deconv,
             spin=spin,
+            **({"nest": True} if self.scheme == "nest" else {}),
         )
         return m
+
+    # -- one page -> position map and shear map -------------------------------------
+    def new_page_stats(self):
+        """zeroed float64[8] accumulator for :meth:`map_page` (see ``hcu_map_page`` in include/heracles_cuda.h)"""
+        return DeviceArray.zeros(self._ctx, (8,))
+
+    def map_page(self, lon, lat, w=None, g1=None, g2=None, *, pos=None, she=None, stats=None) -> None:
+        """
+        One catalogue page into the position map AND the shear map of a tomographic bin in one pass: what the
+        reference does with two ``map_values`` calls from two Field objects that read the same lon / lat / weight
+        columns (``heracles/fields.py:262-271`` and ``:420-433``):
+
+            pos[ipix] += w;   she[0, ipix] += w g1;   she[1, ipix] += w g2
+
+        ``w=None`` means unit weights.  ``stats`` (from :meth:`new_page_stats`) accumulates the running sums the
+        Field layer keeps per page -- rows, sum w, sum w^2 for the positions; rows with w != 0, sum w, sum w^2,
+        sum w^2 (g1^2 + g2^2) for the shears; rows with NaN -- see :func:`page_means`.
+        """
+        lon, lat = _native(lon), _native(lat)
+        n = lon.size
+        cols = [None if c is None else _native(c) for c in (w, g1, g2)]
+        for c in [lat] + [c for c in cols if c is not None]:
+            if c.size != n:
+                raise ValueError("columns differ in size")
+        if she is not None and (cols[1] is None or cols[2] is None):
+            raise ValueError("the shear map needs g1 and g2")
+        for m, lead in ((pos, ()), (she, (2,))):
+            if m is not None and (not isinstance(m, DeviceArray) or m.device_ptr is None or m.shape != (*lead, self.npix)):
+                raise ValueError("maps must come from this mapper's create()")
+            if m is not None:
+                m.to_device()
+        ptr = lambda a: c_vp(_ptr(a)) if a is not None else c_vp(0)  # noqa: E731
+        _lib.check(
+            self._ctx.lib.hcu_map_page(
+                self._ctx.handle, self.__nside, 1 if self.scheme == "nest" else 0, ptr(lon), ptr(lat), ptr(cols[0]),
+                ptr(cols[1]), ptr(cols[2]), n, c_vp(pos.device_ptr if pos is not None else 0),
+                c_vp(she.device_ptr if she is not None else 0), self.npix, c_vp(stats.device_ptr if stats is not None else 0),
+            )
+        )
+        if self.sync:
+            bad = self._ctx.bad_rows()  # synchronises
+            if bad:
+                raise ValueError("THETA is out of range [0,pi]")
+
+    @staticmethod
+    def page_means(stats):
+        """
+        ``(ngal, wmean, w2mean)`` of the positions and ``(ngal, wmean, w2mean, var)`` of the shears from a
+        :meth:`map_page` accumulator: the values the reference's running means converge to
+        (``heracles/fields.py:269-271, 430-433``); raises like ``CatalogPage.get`` if a NaN was seen.
+        """
+        s = np.array(np.asarray(stats), dtype=np.float64)
+        if s[7]:
+            raise ValueError("invalid values in catalogue page columns")
+        pos = (int(s[0]), s[1] / s[0], s[2] / s[0]) if s[0] else (0, 0.0, 0.0)
+        she = (int(s[3]), s[4] / s[3], s[5] / s[3], s[6] / s[3]) if s[3] else (0, 0.0, 0.0, 0.0)
+        return pos, she
 
     # -- map_values -------------------------------------------------------------
     def map_values(self, lon, lat, data, values, spin: int = 0) -> None:
@@ -196,8 +379,8 @@ class CudaHealpixMapper:
         flags = 1 if self.aggregate else 0
         _lib.check(
             self._ctx.lib.hcu_map_values(
-                self._ctx.handle, self.__nside, 0, c_vp(_ptr(lon)), c_vp(_ptr(lat)), c_vp(_ptr(values)),
-                n, nv, n, c_vp(dptr), npix, flags,
+                self._ctx.handle, self.__nside, 1 if self.scheme == "nest" else 0, c_vp(_ptr(lon)), c_vp(_ptr(lat)),
+                c_vp(_ptr(values)), n, nv, n, c_vp(dptr), npix, flags,
             )
         )
         if self.sync:
@@ -261,6 +444,8 @@ class CudaHealpixMapper:
         nalm = (lmax + 1) * (lmax + 2) // 2
         fl = self._fl(spin)
         alm = DeviceArray.zeros(self._ctx, (*lead, nalm), dtype=np.complex128)
+        data = self._ring_view(data)
+        self._apply_modes()
         if isinstance(data, DeviceArray) and data.device_ptr is not None:
             data.to_device()
             mptr = data.device_ptr
@@ -268,8 +453,6 @@ class CudaHealpixMapper:
             data = _native(data)
             mptr = _ptr(data)
         pw = self._pixel_weights
-        if pw is not None:
-            pw = _native(pw)
         _lib.check(
             self._ctx.lib.hcu_map2alm(
                 self._ctx.handle, self.__nside, lmax, spin, nmaps, c_vp(mptr), npix,

@@ -37,8 +37,7 @@ def transform_maps(mapper: CudaHealpixMapper, maps, spin: int = 0):
     nalm = (lmax + 1) * (lmax + 2) // 2
     fl = mapper._fl(spin)
     pw = mapper._pixel_weights
-    if pw is not None:
-        pw = _native(pw)
+    mapper._apply_modes()
     keep = []
     rows_in, rows_out, alms = [], [], []
     for m in maps:
@@ -47,6 +46,7 @@ def transform_maps(mapper: CudaHealpixMapper, maps, spin: int = 0):
         lead = m.shape[:-1]
         if spin == 2 and (len(lead) == 0 or lead[-1] != 2):
             raise ValueError("spin-2 data must have shape (..., 2, npix)")
+        m = mapper._ring_view(m)
         if isinstance(m, DeviceArray) and m.device_ptr is not None:
             m.to_device()
             src = m
@@ -80,7 +80,7 @@ def transform_maps(mapper: CudaHealpixMapper, maps, spin: int = 0):
 def _group_key(mapper):
     return (
         id(mapper.context), mapper.nside, mapper.lmax, mapper.deconvolve, mapper.niter,
-        id(mapper._pixwin), id(mapper._pixel_weights),
+        id(mapper._pixwin), id(mapper._pixel_weights), mapper.weights_mode, mapper.scheme,
     )
 
 

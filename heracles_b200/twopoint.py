@@ -2,8 +2,8 @@
 alm -> Cl on the device: ``alm2cl`` with the reference's signature and block
 output (``heracles/twopoint.py:63-101``) and an ``angular_power_spectra`` that
 keeps the reference's pair selection, key order, metadata and bias rules
-(``heracles/twopoint.py:173-299``) while every spectrum comes from the batched
-``hcu_alm2cl`` kernel.
+(``heracles/twopoint.py:173-299``) while every spectrum comes from ONE batched
+``hcu_alm2cl_rows`` launch over all alm.
 """
 
 from __future__ import annotations
@@ -75,8 +75,33 @@ def _toc_match(key, include, exclude):
     return True
 
 
-def _debias(cl, bias, md):
-    """twopoint._debias_cl for non-deconvolved HEALPix kernels or explicit pixel windows"""
+def _pixwin_for(nside, lmax, pixwin):
+    """(pw_T, pw_P) for the shot-noise debiasing: the caller's arrays, else HEALPix' table under DATAPATH / healpy"""
+    if pixwin is not None:
+        if isinstance(pixwin, np.ndarray) and pixwin.ndim == 1:
+            return pixwin, pixwin
+        return pixwin
+    from .mapper import CudaHealpixMapper, read_pixwin_fits
+    import os
+
+    try:
+        import healpy
+
+        return healpy.pixwin(nside, lmax=lmax, pol=True)
+    except Exception:
+        pass
+    if CudaHealpixMapper.DATAPATH:
+        path = os.path.join(CudaHealpixMapper.DATAPATH, "pixel_window_n%04d.fits" % nside)
+        if os.path.exists(path):
+            return read_pixwin_fits(path)
+    raise RuntimeError(
+        "debiasing deconvolved HEALPix spectra needs the pixel window: pass pixwin=(pw_T, pw_P) (the arrays the mapper "
+        "deconvolved with) to angular_power_spectra, set CudaHealpixMapper.DATAPATH, or use debias=False"
+    )
+
+
+def _debias(cl, bias, md, pixwin=None):
+    """twopoint._debias_cl (heracles/twopoint.py:104-170); no device context is touched here"""
     spin1, spin2 = md.get("spin_1", 0), md.get("spin_2", 0)
     lmin = max(abs(spin1), abs(spin2))
     lmax = cl.shape[-1] - 1
@@ -90,9 +115,7 @@ def _debias(cl, bias, md):
             nside = md.get(f"nside_{i}")
             deconv = md.get(f"deconv_{i}", True)
             if nside is not None and deconv:
-                from .mapper import CudaHealpixMapper
-
-                pw = CudaHealpixMapper(nside, lmax, deconvolve=True)._get_pixwin()
+                pw = _pixwin_for(nside, lmax, pixwin)
                 pw = pw[0] if s == 0 else pw[1] if s == 2 else None
                 if pw is not None:
                     bl[..., lmin:] /= np.asarray(pw)[lmin : lmax + 1]
@@ -112,12 +135,17 @@ def angular_power_spectra(
     exclude=None,
     out=None,
     context=None,
+    pixwin=None,
 ):
     """
     Drop-in for ``heracles.twopoint.angular_power_spectra``.  Keys, ordering,
     metadata (``*_1`` / ``*_2``, ``bias``) and the debiasing follow the
-    reference; the spectra are computed on the device, one ``hcu_alm2cl`` block
-    per pair of alm arrays, with the alm resident in managed memory.
+    reference (``heracles/twopoint.py:198-290``); the reference calls ``alm2cl`` once per pair of alm arrays
+    (``:243``), here ALL pairs come from ONE ``hcu_alm2cl_rows`` launch over the device-resident alm (every alm is
+    read once per 4 x 4 tile of spectra) and each pair's block is sliced out of it.  Mixed ``lmax`` or more than 64
+    alm rows fall back to one ``hcu_alm2cl`` per pair.
+    ``pixwin``: the ``(pw_T, pw_P)`` the mapper deconvolved with -- used for the bias of deconvolved spectra
+    (the reference asks healpy for it, ``twopoint.py:152-161``).
     When the ``heracles`` package is importable the results are wrapped in its
     ``Result`` type and optionally binned, exactly as upstream does.
     """
@@ -136,26 +164,13 @@ def angular_power_spectra(
         raise RuntimeError("binning needs the heracles package (heracles.result.binned)")
 
     cls = {} if out is None else out
+
+    # ---- pass 1: the reference's pair selection (twopoint.py:204-236) ----
     names = set()
-    staged: dict = {}
-
-    def dev(a):
-        # the entry keeps `a` itself alive: a lazily loading alm mapping hands out a NEW array per
-        # access, and a freed array's id() would otherwise be recycled for a different (k, i)
-        key = id(a)
-        if key not in staged:
-            if isinstance(a, DeviceArray) and a.device_ptr is not None:
-                staged[key] = (a, a)
-            else:  # host alm: upload once, reuse for every pair it takes part in
-                h = np.ascontiguousarray(a, dtype=np.complex128)
-                d = DeviceArray.zeros(ctx, h.shape, dtype=np.complex128)
-                ctx.memcpy(d.device_ptr, h.__array_interface__["data"][0], h.nbytes)
-                ctx.synchronize()
-                staged[key] = (a, d)
-        return staged[key][1]
-
+    todo = []
+    seen = set(cls)
     for (k1, i1), (k2, i2) in pairs:
-        if (k1, k2, i1, i2) in cls or (k2, k1, i2, i1) in cls:
+        if (k1, k2, i1, i2) in seen or (k2, k1, i2, i1) in seen:
             continue
         swapped = (k1, k2) not in names and (k2, k1) in names
         if swapped:
@@ -163,12 +178,69 @@ def angular_power_spectra(
             k1, k2 = k2, k1
         if not _toc_match((k1, k2, i1, i2), include, exclude):
             continue
-        if swapped:
-            alm1, alm2 = alms2[k1, i1], alms[k2, i2]
-        else:
-            alm1, alm2 = alms[k1, i1], alms2[k2, i2]
+        # which mapping each side comes from (twopoint.py:232-236)
+        src1, src2 = (1, 0) if swapped else (0, 1)
+        todo.append((k1, k2, i1, i2, src1, src2))
+        seen.add((k1, k2, i1, i2))
+        names.add((k1, k2))
 
-        cl = alm2cl(dev(alm1), dev(alm2), lmax=lmax, context=ctx)
+    # ---- the alm arrays taking part: fetched ONCE per (mapping, key) -- a lazily loading mapping returns a new
+    # array per access -- and kept alive together with their device copy until the end of the call ----
+    maps_ = (alms, alms2)
+    same_mapping = alms2 is alms
+    arrays = {}
+
+    def entry(src, k, i):
+        key = (0 if same_mapping else src, k, i)
+        if key not in arrays:
+            a = maps_[src][k, i]
+            if isinstance(a, DeviceArray) and a.device_ptr is not None and a.dtype == np.complex128:
+                a.to_device()
+                d = a
+            else:  # host alm: upload once, reuse for every pair it takes part in
+                h = np.ascontiguousarray(a, dtype=np.complex128)
+                d = DeviceArray.zeros(ctx, h.shape, dtype=np.complex128)
+                ctx.memcpy(d.device_ptr, h.__array_interface__["data"][0], h.nbytes)
+            arrays[key] = (a, d)
+        return arrays[key]
+
+    for k1, k2, i1, i2, s1_, s2_ in todo:
+        entry(s1_, k1, i1)
+        entry(s2_, k2, i2)
+    ctx.synchronize()
+
+    # ---- one Gram block over all rows when the arrays share lmax ----
+    gram = None
+    row0 = {}
+    lmaxes = {alm2lmax(d) for _, d in arrays.values()}
+    nrows = sum(d.size // d.shape[-1] for _, d in arrays.values())
+    if arrays and len(lmaxes) == 1 and nrows <= 64:
+        import ctypes
+
+        lin = lmaxes.pop()
+        lout = lin if lmax is None else min(lmax, lin)
+        ptrs = []
+        for key, (_, d) in arrays.items():
+            row0[key] = len(ptrs)
+            n = d.shape[-1]
+            ptrs.extend(d.device_ptr + 16 * n * r for r in range(d.size // n))
+        tab = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        dev = DeviceArray.zeros(ctx, (len(ptrs), len(ptrs), lout + 1), dtype=np.float64)
+        _lib.check(ctx.lib.hcu_alm2cl_rows(ctx.handle, len(ptrs), tab, lin, lout, c_vp(dev.device_ptr)))
+        ctx.synchronize()
+        gram = np.array(dev._host(), copy=True)
+        del dev
+
+    # ---- pass 2: metadata, bias, Result (twopoint.py:238-290) ----
+    for k1, k2, i1, i2, s1_, s2_ in todo:
+        key1, key2 = (0 if same_mapping else s1_, k1, i1), (0 if same_mapping else s2_, k2, i2)
+        (alm1, d1), (alm2, d2) = arrays[key1], arrays[key2]
+        if gram is not None:
+            n1, n2 = d1.size // d1.shape[-1], d2.size // d2.shape[-1]
+            r1, r2 = row0[key1], row0[key2]
+            cl = np.array(gram[r1:r1 + n1, r2:r2 + n2], copy=True).reshape(*d1.shape[:-1], *d2.shape[:-1], gram.shape[-1])
+        else:
+            cl = alm2cl(d1, d2, lmax=lmax, context=ctx)
 
         md1 = alm1.dtype.metadata or {}
         md2 = alm2.dtype.metadata or {}
@@ -188,12 +260,11 @@ def angular_power_spectra(
         if bias is not None:
             md["bias"] = bias
         if debias and bias is not None:
-            _debias(cl, bias, md)
+            _debias(cl, bias, md, pixwin)
         update_metadata(cl, **md)
         if Result is not None:
             cl = Result(cl, spin=(s1, s2), axis=-1)
             if bins is not None:
                 cl = binned(cl, bins, weights)
         cls[k1, k2, i1, i2] = cl
-        names.add((k1, k2))
     return cls

@@ -121,6 +121,7 @@ int hcu_scale(hcu_ctx *ctx, double *x, int64_t n, double a);          /* x *= a 
 int hcu_divide(hcu_ctx *ctx, double *x, int64_t n, double a);         /* x /= a        */
 int hcu_axpy(hcu_ctx *ctx, double *y, const double *x, double a, int64_t n); /* y += a x */
 int hcu_add_scalar(hcu_ctx *ctx, double *x, int64_t n, double a);     /* x += a        */
+int hcu_multiply(hcu_ctx *ctx, double *out, const double *a, const double *b, int64_t n); /* out = a b (masks) */
 
 /* hp.reorder(map, r2n / n2r): RING <-> NEST order of a whole map (out of place; device or managed memory).
  * The transform works on RING maps; a mapper configured for NEST maps reorders before hcu_map2alm. */
@@ -143,6 +144,12 @@ int hcu_map2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nmaps,
                 const double *maps, int64_t map_stride,
                 const double *ring_weights, const double *pixel_weights,
                 int niter, const double *fl, void *alm, int64_t alm_stride);
+
+/* How pixel_weights enter an iterated transform (niter > 0):
+ *   per_pass = 0 (default, healpy's use_pixel_weights=True): the map is multiplied by the weights once and the
+ *                Jacobi iterations run on the weighted map with unit weights, alm += A(W map - S(alm));
+ *   per_pass = 1: the weights are part of the quadrature of every analysis pass, alm += A(W (map - S(alm))). */
+int hcu_set_weights_mode(hcu_ctx *ctx, int per_pass);
 
 /* Same transform for rows that are NOT contiguous in memory: maps[c] / alm[c]
  * are per-row pointers.  This is what lets one call batch the maps of many
@@ -209,6 +216,10 @@ int hcu_phase2map(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp, const double
 int hcu_alm2cl(hcu_ctx *ctx, int na, const void *a, int64_t stride_a,
                int lmax_a, int nb, const void *b, int64_t stride_b, int lmax_b,
                int lmax_out, double *cl);
+/* The symmetric block of ALL pairs of nrows alm rows that live in SEPARATE allocations (rows[i]: device or managed
+ * complex128[nalm], all with the same lmax): cl[(i*nrows + j)*(lout+1) + l].  angular_power_spectra calls alm2cl
+ * once per pair of alm arrays (heracles/twopoint.py:198-243); this computes all of them in one launch.  nrows <= 64. */
+int hcu_alm2cl_rows(hcu_ctx *ctx, int nrows, const void *const *rows, int lmax, int lmax_out, double *cl);
 /* the same sum restricted to m = m_offset (mod m_step): the partial spectra of one rank of the
  * multi-GPU path, whose alm are m-distributed (summing them over the ranks gives hcu_alm2cl) */
 int hcu_alm2cl_mslice(hcu_ctx *ctx, int na, const void *a, int64_t stride_a,

@@ -205,11 +205,11 @@ def test_deconvolution_filter_cache_is_keyed_by_content():
 
 
 def test_angular_power_spectra_staging_keeps_lazy_alms_alive():
-    """the upload cache of angular_power_spectra must not be fooled by recycled ids of
-    lazily loaded alm (a mapping that returns a NEW array per access, as heracles' AlmFits does)"""
+    """angular_power_spectra must not key its upload cache on id() of arrays it does not keep alive
+    (a lazily loading alm mapping returns a NEW array per access); the functional test is tests/test_gpu_cl.py"""
     import inspect
 
     from heracles_b200 import twopoint
 
     src = inspect.getsource(twopoint.angular_power_spectra)
-    assert "staged[key] = (a, d)" in src and "staged[key] = (a, a)" in src
+    assert "id(" not in src and "arrays[key] = (a, d)" in src

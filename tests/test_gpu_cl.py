@@ -129,3 +129,56 @@ def test_alm2cl_mslice_parts_sum_to_the_whole(hb, ctx):
         parts += np.asarray(cl)
     scale = np.abs(full).max()
     assert np.abs(parts - full).max() < 1e-13 * scale
+
+
+def test_angular_power_spectra_one_gram_and_lazy_alms(hb, oracle):
+    """every pair from ONE hcu_alm2cl_rows launch; alm mappings that load lazily (a NEW array per access, as the
+    reference's AlmFits does -- 'alms might lazy-load from file', heracles/twopoint.py:233) must not confuse the staging"""
+    lmax = 40
+    na = (lmax + 1) * (lmax + 2) // 2
+    rng = np.random.default_rng(31)
+    store = {}
+    for k, i, spin in [("POS", 0, 0), ("POS", 1, 0), ("SHE", 0, 2), ("SHE", 1, 2)]:
+        a = rng.standard_normal((2, na) if spin else na) + 1j * rng.standard_normal((2, na) if spin else na)
+        hb.update_metadata(a, spin=spin, nside=16)
+        store[k, i] = a
+
+    class Lazy(dict):
+        loads = 0
+
+        def __getitem__(self, key):
+            Lazy.loads += 1
+            a = np.array(dict.__getitem__(self, key))  # a fresh array every time
+            hb.update_metadata(a, **dict.__getitem__(self, key).dtype.metadata)
+            return a
+
+    cls = hb.angular_power_spectra(Lazy(store), debias=False)
+    assert Lazy.loads == 4  # one load per alm, not one per pair
+    assert list(cls) == [("POS", "POS", 0, 0), ("POS", "POS", 0, 1), ("POS", "SHE", 0, 0), ("POS", "SHE", 0, 1),
+                         ("POS", "POS", 1, 1), ("POS", "SHE", 1, 0), ("POS", "SHE", 1, 1), ("SHE", "SHE", 0, 0),
+                         ("SHE", "SHE", 0, 1), ("SHE", "SHE", 1, 1)]
+    for (k1, k2, i1, i2), cl in cls.items():
+        ref = oracle.alm2cl(store[k1, i1], store[k2, i2])
+        assert np.asarray(cl).shape == ref.shape
+        assert np.abs(np.asarray(cl) - ref).max() < 1e-13 * np.abs(ref).max() + 1e-30
+    # two mappings (product) and a smaller lmax
+    cl2 = hb.angular_power_spectra(store, {("POS", 7): store["POS", 1]}, lmax=20, debias=False)
+    assert list(cl2) == [("POS", "POS", 0, 7), ("POS", "POS", 1, 7), ("SHE", "POS", 0, 7), ("SHE", "POS", 1, 7)]
+    npt.assert_allclose(np.asarray(cl2["SHE", "POS", 0, 7]), oracle.alm2cl(store["SHE", 0], store["POS", 1], lmax=20), rtol=0, atol=1e-13)
+
+
+def test_debias_uses_the_callers_pixel_window(hb):
+    """ADVICE r1: the bias of deconvolved spectra is divided by the window the MAPPER used, passed by the caller;
+    no mapper / device context is created behind the scenes and no healpy table is needed"""
+    lmax = 12
+    na = (lmax + 1) * (lmax + 2) // 2
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal(na) + 0j
+    hb.update_metadata(a, spin=0, nside=8, kernel="healpix", deconv=True, fsky=1.0, musq=1.0, dens=4.0)
+    pw = 1.0 / (1.0 + 0.05 * np.arange(lmax + 1))
+    raw = hb.angular_power_spectra({("P", 0): a}, debias=False)["P", "P", 0, 0]
+    deb = hb.angular_power_spectra({("P", 0): a}, pixwin=(pw, pw))["P", "P", 0, 0]
+    npt.assert_allclose(np.asarray(raw) - np.asarray(deb), 0.25 / pw, rtol=1e-13)
+    assert np.asarray(deb).dtype.metadata["bias"] == 0.25
+    with pytest.raises(RuntimeError, match="pixel window"):
+        hb.angular_power_spectra({("P", 0): a})

@@ -203,3 +203,59 @@ def test_resample(hb, oracle):
     up = np.asarray(mapper.resample(small))
     parent = oracle.nest2ring(4, oracle.ring2nest(8, np.arange(12 * 64)) // 4)
     npt.assert_array_equal(up, small[parent])
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_map_page_fused(hb, oracle, pinned):
+    """hcu_map_page: POS + SHE maps of a tomographic bin from ONE pass over the page (5 columns instead of 7),
+    with the Field layer's running sums reduced on the device (heracles/fields.py:262-271, 420-433)"""
+    nside, n = 64, 300_000
+    rng = np.random.default_rng(77)
+    lon = rng.uniform(-180, 540, n)
+    lat = np.degrees(np.arcsin(rng.uniform(-1, 1, n)))
+    w = rng.uniform(0.5, 1.5, n)
+    w[rng.integers(0, n, 1000)] = 0.0  # page.delete(page[wcol] == 0) for the shears, fields.py:420-421
+    g1, g2 = rng.normal(0, 0.3, (2, n))
+    mapper = hb.CudaHealpixMapper(nside, deconvolve=False)
+    ctx = mapper.context
+    cols = [lon, lat, w, g1, g2]
+    if pinned:  # pinned pages go straight to cudaMemcpyAsync, pageable ones through the staging slots
+        from heracles_b200 import _lib
+        import ctypes
+
+        keep = []
+        for i, c in enumerate(cols):
+            p = ctx.malloc_pinned(c.nbytes)
+            buf = np.ctypeslib.as_array((ctypes.c_double * c.size).from_address(p))
+            buf[:] = c
+            keep.append(p)
+            cols[i] = buf
+    pos, she, stats = mapper.create(), mapper.create(2, spin=2), mapper.new_page_stats()
+    # two "pages"
+    h = n // 3
+    mapper.map_page(*(c[:h] for c in cols), pos=pos, she=she, stats=stats)
+    mapper.map_page(*(c[h:] for c in cols), pos=pos, she=she, stats=stats)
+    ref_pos = np.zeros(12 * nside**2)
+    ref_she = np.zeros((2, 12 * nside**2))
+    oracle.map_values(nside, lon, lat, ref_pos, w)
+    nz = w != 0
+    oracle.map_values(nside, lon[nz], lat[nz], ref_she, np.stack([w * g1, w * g2])[:, nz])
+    npt.assert_allclose(np.asarray(pos), ref_pos, rtol=0, atol=1e-12 * ref_pos.max())
+    npt.assert_allclose(np.asarray(she), ref_she, rtol=0, atol=1e-12 * np.abs(ref_she).max())
+    (ng0, wm0, w2m0), (ng2, wm2, w2m2, var) = hb.CudaHealpixMapper.page_means(stats)
+    assert ng0 == n and ng2 == int(nz.sum())
+    npt.assert_allclose([wm0, w2m0], [w.mean(), (w**2).mean()], rtol=1e-13)
+    npt.assert_allclose([wm2, w2m2, var], [w[nz].mean(), (w[nz] ** 2).mean(), ((w * g1) ** 2 + (w * g2) ** 2)[nz].mean()], rtol=1e-13)
+    # positions only, unit weights (fields.py:265); NaN rows are what CatalogPage.get raises on
+    pos2, st2 = mapper.create(), mapper.new_page_stats()
+    lon2 = lon.copy()
+    lon2[5] = np.nan
+    mapper.map_page(lon2, lat, pos=pos2, stats=st2)
+    ref2 = np.zeros(12 * nside**2)
+    oracle.map_values(nside, np.delete(lon, 5), np.delete(lat, 5), ref2, np.ones(n - 1))
+    npt.assert_array_equal(np.asarray(pos2), ref2)
+    with pytest.raises(ValueError, match="invalid values"):
+        hb.CudaHealpixMapper.page_means(st2)
+    if pinned:
+        for p in keep:
+            ctx.free(p)
