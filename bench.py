@@ -185,16 +185,18 @@ class Pipeline:
         self.dist = None
         if world > 1:
             # ring-block / m-distributed transform over the ranks (heracles_b200/dist.py)
-            from heracles_b200.dist import DistributedTransform, ShardPlan, StagedKernels
+            from heracles_b200.dist import DistributedTransform, ShardPlan, make_lanes
 
             self.plan = ShardPlan(nside, lmax, world)
-            self.kernels = StagedKernels(self.ctx, nside, lmax)
-            self.dist = DistributedTransform(self.kernels, self.plan, rank, niter=niter, device=torch.device("cuda"))
-            # a communicator of its own for the map all-reduce that overlaps the spin-0 transform (collectives
-            # of ONE communicator run in issue order, so the transform's all-to-all would queue behind it)
-            from heracles_b200.dist import _reduce_group
-
-            self.reduce_group = _reduce_group()
+            # two lanes: the FFT / all-to-all stages of one Legendre batch run under the Legendre kernels of another;
+            # lane 1's communicator also carries the asynchronous SHE map reduction (collectives of ONE communicator
+            # run in issue order, so it would otherwise queue in front of the spin-0 exchange)
+            self.lanes = make_lanes(self.ctx, nside, lmax, int(os.environ.get("HCU_BENCH_LANES", "2")))
+            for lane in self.lanes:
+                lane.k.ctx.set_timing(True)
+            self.kernels = self.lanes[0].k
+            self.dist = DistributedTransform(self.kernels, self.plan, rank, niter=niter, device=torch.device("cuda"), lanes=self.lanes)
+            self.reduce_group = self.lanes[-1].group
         self.make_catalogue()
 
     # synthetic catalogue: uniform positions, w ~ U(0.5,1.5), g ~ N(0,0.3)  
@@ -335,15 +337,18 @@ class Pipeline:
                 # the spin-0 transform runs; the linear normalisations come first, "- vis" after the sum
                 import torch.distributed as dist
 
+                from heracles_b200.dist import ReadyOnce
+
                 self.stage_normalise(scale=True, shift=False)
                 dist.all_reduce(self.maps[:self.nbins])
                 work = dist.all_reduce(self.maps[self.nbins:], group=self.reduce_group, async_op=True) if self.cfg["she"] else None
                 self.stage_normalise(scale=False, shift=True)
                 ev[2].record()
-                self.stage_transform(stats, spins=(0,))
-                if work is not None:
-                    work.wait()
-                    self.stage_transform(stats, spins=(2,))
+                nb = self.nbins
+                jobs = [(self.maps[:nb], 0, self.alm[:nb], None)]
+                if self.cfg["she"]:
+                    jobs.append((self.maps[nb:], 2, self.alm[nb:], None))
+                self.dist.map2alm_jobs(jobs, {2: ReadyOnce(work)})
             else:
                 self.stage_normalise()
                 ev[2].record()
@@ -863,9 +868,10 @@ def main():
         pipe.step(dict(stats))
     barrier()
     if pipe.dist is not None:
-        pipe.kernels.timing = True
+        for lane in pipe.lanes:
+            lane.k.timing = True
         pipe.dist.timing = True
-        work0 = ctx.sht_work()
+        work0 = [sum(x) for x in zip(*(lane.k.ctx.sht_work() for lane in pipe.lanes))]
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ctx.launch_count()
@@ -881,8 +887,11 @@ def main():
     if pipe.dist is not None:
         # the staged path: Legendre analysis time from CUDA events around hcu_phase2alm, executed cells
         # from the kernels' work counters (equal shares for the batches of a pass)
-        stats["leg_ana_ms"] = pipe.kernels.analysis_ms()
-        pipe.kernels.timing = False
+        # with two lanes the Legendre kernels of one batch share the SMs with the FFT / exchange of another, so these
+        # event-bracketed times overlap and their sum can exceed the step
+        stats["leg_ana_ms"] = sum(lane.k.analysis_ms() for lane in pipe.lanes)
+        for lane in pipe.lanes:
+            lane.k.timing = False
         # per-rank stage times of the distributed transform (a2a includes waiting for the slowest rank)
         st = pipe.dist.stage_ms()
         pipe.dist.timing = False
@@ -893,7 +902,7 @@ def main():
         dist_stage = {k: [round(float(a[i]) / args.steps, 1) for a in allt] for i, k in enumerate(names)}
         stats["fft_ms"] = st.get("fft", 0.0) + st.get("ifft", 0.0)
         stats["leg_syn_ms"] = st.get("leg_syn", 0.0)
-        work1 = ctx.sht_work()
+        work1 = [sum(x) for x in zip(*(lane.k.ctx.sht_work() for lane in pipe.lanes))]
         per_cell, nbat = pipe.dist_flops_per_cell()
         rec, acc = (work1[0] - work0[0]) / nbat, (work1[1] - work0[1]) / nbat
         nb = cfg["nbins"]

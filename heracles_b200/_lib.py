@@ -208,6 +208,20 @@ class Context:
 _contexts: dict[int, Context] = {}
 
 
+_extra: dict = {}
+
+
+def extra_context(device: int, index: int) -> Context:
+    """additional library contexts on a device (own stream, workspaces, cuFFT plans): the lanes of the multi-GPU path"""
+    with _lock:
+        ctx = _extra.get((device, index))
+    if ctx is None:
+        ctx = Context(device)
+        with _lock:
+            _extra[(device, index)] = ctx
+    return ctx
+
+
 def get_context(device: int | None = None) -> Context:
     """process-wide context per device (LOCAL_RANK selects the default device)"""
     if device is None:

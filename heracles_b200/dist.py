@@ -31,7 +31,7 @@ import hashlib
 
 import numpy as np
 
-__all__ = ["ShardPlan", "StagedKernels", "DistributedTransform", "reduce_maps", "allreduce_cl", "as_torch", "DistributedPipeline"]
+__all__ = ["ShardPlan", "StagedKernels", "Lane", "make_lanes", "DistributedTransform", "reduce_maps", "allreduce_cl", "as_torch", "DistributedPipeline"]
 
 
 # ---------------------------------------------------------------------------------------
@@ -207,6 +207,28 @@ class StagedKernels:
 # ---------------------------------------------------------------------------------------
 # the distributed transform
 # ---------------------------------------------------------------------------------------
+class Lane:
+    """
+    One independent instruction stream for whole Legendre batches: its own stage kernels (i.e. its own library context
+    with its workspaces and cuFFT plans), process group (collectives of ONE communicator run in issue order), CUDA
+    stream and exchange buffers.  With two lanes the ring FFTs and the all-to-all of one batch run while the other
+    batch is in its (FP64-bound) Legendre kernels.
+    """
+
+    def __init__(self, kernels, group=None, stream=None):
+        self.k, self.group, self.stream = kernels, group, stream
+        self.ws = {}
+
+    def context(self):
+        import contextlib
+
+        if self.stream is None:
+            return contextlib.nullcontext()
+        import torch
+
+        return torch.cuda.stream(self.stream)
+
+
 class DistributedTransform:
     """
     ``hp.map2alm`` (``heracles/healpy.py:183-189``) over the ranks of a process group.
@@ -215,9 +237,11 @@ class DistributedTransform:
         block hold the (rank-summed) map; spin 2: rows are (Q, U) pairs.
     alm  : tensor ``[ncomp, nalm]`` complex128; on return the entries whose m this rank owns
         hold the result, every other entry is zero (so a SUM all-reduce gathers them).
+    lanes : optional list of :class:`Lane`; the Legendre batches of a call are dealt out to the lanes and run
+        concurrently (default: one lane on the caller's stream).
     """
 
-    def __init__(self, kernels, plan: ShardPlan, rank: int, group=None, niter: int = 3, device=None):
+    def __init__(self, kernels, plan: ShardPlan, rank: int, group=None, niter: int = 3, device=None, lanes=None):
         import torch
 
         self.k, self.plan, self.rank, self.group, self.niter = kernels, plan, int(rank), group, int(niter)
@@ -226,6 +250,7 @@ class DistributedTransform:
         self.mlist_me = torch.from_numpy(plan.mlists[rank].copy()).to(dev)
         self.m_all = torch.from_numpy(plan.m_all.copy()).to(dev)
         self.mpos = torch.from_numpy(plan.mpos.copy()).to(dev)
+        self.lanes = list(lanes) if lanes else [Lane(kernels, group, None)]
         self._ws = {}
         self.exchanged_bytes = 0
         self.timing = False   # CUDA events around the stages (device tensors only)
@@ -254,7 +279,8 @@ class DistributedTransform:
         return _T()
 
     def stage_ms(self):
-        """device milliseconds per stage since the last call (synchronises)"""
+        """device milliseconds per stage since the last call (synchronises); with two lanes the stages of
+        different batches overlap, so the sum exceeds the elapsed time"""
         import torch
 
         torch.cuda.synchronize()
@@ -263,110 +289,171 @@ class DistributedTransform:
         return out
 
     # -- helpers ------------------------------------------------------------------------------
-    def _buf(self, name, n):
+    def _buf(self, lane, name, n):
         import torch
 
-        t = self._ws.get(name)
+        t = lane.ws.get(name)
         if t is None or t.numel() < n:
             t = torch.empty(n, dtype=torch.float64, device=self.device)
-            self._ws[name] = t
+            lane.ws[name] = t
         return t[:n]
 
     def release(self):
         self._ws.clear()
+        for lane in self.lanes:
+            lane.ws.clear()
 
-    def _all_to_all(self, out, inp, out_splits, in_splits):
+    def _all_to_all(self, lane, out, inp, out_splits, in_splits):
         import torch.distributed as dist
 
         if self.plan.world == 1:
             out.copy_(inp)
             return
-        dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=self.group)
+        dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=lane.group)
         self.exchanged_bytes += 8 * (sum(in_splits) - in_splits[self.rank])
 
-    # -- one analysis pass over a batch: alm += A(maps) -------------------------------------------
-    def _analysis(self, maps, spin, alm):
+    # -- one analysis pass over a batch: alm += A(maps); yields between its stages ---------------------
+    def _analysis(self, lane, maps, spin, alm):
         plan, g, W = self.plan, self.rank, self.plan.world
+        k = lane.k
         nb = maps.shape[0]
         lo, hi = plan.rp_range(g)
         nrp_me, nm_me = hi - lo, len(plan.mlists[g])
         per = nb * 4
-        send = self._buf("send", (plan.lmax + 1) * nrp_me * per)
+        send = self._buf(lane, "send", (plan.lmax + 1) * nrp_me * per)
         with self._mark("fft"):
-            self.k.map2phase(maps, lo, hi, self.m_all, send)
+            k.map2phase(maps, lo, hi, self.m_all, send)
+        yield
         in_splits = [len(plan.mlists[d]) * nrp_me * per for d in range(W)]
         out_splits = [nm_me * plan.nrp_of(s) * per for s in range(W)]
-        recv = self._buf("recv", sum(out_splits))
+        recv = self._buf(lane, "recv", sum(out_splits))
         with self._mark("a2a"):
-            self._all_to_all(recv, send, out_splits, in_splits)
+            self._all_to_all(lane, recv, send, out_splits, in_splits)
+        yield
         off = 0
         with self._mark("leg_ana"):
-            if nm_me and hasattr(self.k, "phase2alm_blocks") and W <= 16:
-                self.k.phase2alm_blocks(recv, spin, nb, self.mlist_me, list(plan.rp_bounds), alm)
-                return
-            for s in range(W):
-                slo, shi = plan.rp_range(s)
-                if nm_me and out_splits[s]:
-                    self.k.phase2alm(recv[off:off + out_splits[s]], spin, nb, self.mlist_me, slo, shi, alm)
-                off += out_splits[s]
+            if nm_me and hasattr(k, "phase2alm_blocks") and W <= 16:
+                k.phase2alm_blocks(recv, spin, nb, self.mlist_me, list(plan.rp_bounds), alm)
+            else:
+                for s in range(W):
+                    slo, shi = plan.rp_range(s)
+                    if nm_me and out_splits[s]:
+                        k.phase2alm(recv[off:off + out_splits[s]], spin, nb, self.mlist_me, slo, shi, alm)
+                    off += out_splits[s]
+        yield
 
     # -- one synthesis pass over a batch: maps (local rings) = S(alm) ------------------------------
-    def _synthesis(self, alm, spin, maps):
+    def _synthesis(self, lane, alm, spin, maps):
         plan, g, W = self.plan, self.rank, self.plan.world
+        k = lane.k
         nb = alm.shape[0]
         lo, hi = plan.rp_range(g)
         nrp_me, nm_me = hi - lo, len(plan.mlists[g])
         per = nb * 4
         in_splits = [nm_me * plan.nrp_of(d) * per for d in range(W)]
         out_splits = [len(plan.mlists[s]) * nrp_me * per for s in range(W)]
-        send = self._buf("send", sum(in_splits))
+        send = self._buf(lane, "send", sum(in_splits))
         off = 0
         with self._mark("leg_syn"):
-            if nm_me and hasattr(self.k, "alm2phase_blocks") and W <= 16:
-                self.k.alm2phase_blocks(alm, spin, nb, self.mlist_me, list(plan.rp_bounds), send)
+            if nm_me and hasattr(k, "alm2phase_blocks") and W <= 16:
+                k.alm2phase_blocks(alm, spin, nb, self.mlist_me, list(plan.rp_bounds), send)
             else:
                 for d in range(W):
                     dlo, dhi = plan.rp_range(d)
                     if nm_me and in_splits[d]:
-                        self.k.alm2phase(alm, spin, nb, self.mlist_me, dlo, dhi, send[off:off + in_splits[d]])
+                        k.alm2phase(alm, spin, nb, self.mlist_me, dlo, dhi, send[off:off + in_splits[d]])
                     off += in_splits[d]
-        recv = self._buf("recv", sum(out_splits))
+        yield
+        recv = self._buf(lane, "recv", sum(out_splits))
         with self._mark("a2a"):
-            self._all_to_all(recv, send, out_splits, in_splits)
+            self._all_to_all(lane, recv, send, out_splits, in_splits)
+        yield
         # rows of recv are ordered by source rank = the order of plan.m_all
         with self._mark("ifft"):
-            self.k.phase2map(recv, nb, self.mpos, lo, hi, maps)
+            k.phase2map(recv, nb, self.mpos, lo, hi, maps)
+        yield
+
+    def _batch(self, lane, mb, spin, ab, ready=None):
+        """all passes of one Legendre batch; a generator that yields after every stage it has queued"""
+        import torch
+
+        plan = self.plan
+        ranges = plan.pixel_ranges(self.rank)
+        if ready is not None:
+            ready()  # e.g. the (asynchronous) reduction of these maps over the ranks: this lane's stream waits for it
+        ab.zero_()
+        yield from self._analysis(lane, mb, spin, ab)
+        if self.niter > 0:
+            n = mb.shape[0]
+            resid = self._buf(lane, "resid", n * plan.npix).view(n, plan.npix)
+            for _ in range(self.niter):
+                yield from self._synthesis(lane, ab, spin, resid)
+                for a, b in ranges:  # residual on the pixels of this rank's rings
+                    torch.sub(mb[:, a:b], resid[:, a:b], out=resid[:, a:b])
+                yield from self._analysis(lane, resid, spin, ab)
 
     # -- public -----------------------------------------------------------------------------------
     def map2alm(self, maps, spin: int, alm, fl=None):
+        return self.map2alm_jobs([(maps, spin, alm, fl)])[0]
+
+    def map2alm_jobs(self, jobs, ready=None):
+        """
+        Several transforms at once: ``jobs`` is a list of ``(maps, spin, alm, fl)``.  Their Legendre batches are dealt
+        out to the lanes round robin and the lanes' stage sequences are queued interleaved, so that with two lanes the
+        FFT / exchange stages of one batch overlap the Legendre kernels of another.  ``ready``: optional dict
+        ``spin -> callable`` that makes the CURRENT stream wait until the maps of that spin may be read.
+        """
         import torch
 
-        if spin not in (0, 2):
-            msg = f"spin-{spin} maps not yet supported"
-            raise NotImplementedError(msg)
         plan = self.plan
-        ncomp = maps.shape[0]
-        if maps.shape[-1] != plan.npix or alm.shape != (ncomp, plan.nalm):
-            raise ValueError("maps / alm do not match the plan")
-        if spin == 2 and ncomp % 2:
-            raise ValueError("spin-2 input needs (Q, U) pairs")
-        cap = self.k.batch_size(spin)
-        ranges = plan.pixel_ranges(self.rank)
-        for c0 in range(0, ncomp, cap):
-            c1 = min(ncomp, c0 + cap)
-            mb, ab = maps[c0:c1], alm[c0:c1]
-            ab.zero_()
-            self._analysis(mb, spin, ab)
-            if self.niter > 0:
-                resid = self._buf("resid", (c1 - c0) * plan.npix).view(c1 - c0, plan.npix)
-                for _ in range(self.niter):
-                    self._synthesis(ab, spin, resid)
-                    for a, b in ranges:  # residual on the pixels of this rank's rings
-                        torch.sub(mb[:, a:b], resid[:, a:b], out=resid[:, a:b])
-                    self._analysis(resid, spin, ab)
-        if fl is not None:
-            alm.mul_(self._fl_full(fl))
-        return alm
+        per_lane = [[] for _ in self.lanes]
+        nbatch = 0
+        for maps, spin, alm, fl in jobs:
+            if spin not in (0, 2):
+                msg = f"spin-{spin} maps not yet supported"
+                raise NotImplementedError(msg)
+            ncomp = maps.shape[0]
+            if maps.shape[-1] != plan.npix or alm.shape != (ncomp, plan.nalm):
+                raise ValueError("maps / alm do not match the plan")
+            if spin == 2 and ncomp % 2:
+                raise ValueError("spin-2 input needs (Q, U) pairs")
+            cap = self.lanes[0].k.batch_size(spin)
+            for c0 in range(0, ncomp, cap):
+                c1 = min(ncomp, c0 + cap)
+                per_lane[nbatch % len(self.lanes)].append((maps[c0:c1], spin, alm[c0:c1]))
+                nbatch += 1
+        use_streams = any(lane.stream is not None for lane in self.lanes)
+        start = None
+        if use_streams:
+            start = torch.cuda.Event()
+            start.record()
+
+        def lane_steps(lane, batches):
+            if start is not None and lane.stream is not None:
+                lane.stream.wait_event(start)  # everything queued so far (maps, normalisation) is visible to the lane
+            for mb, spin, ab in batches:
+                yield from self._batch(lane, mb, spin, ab, None if ready is None else ready.get(spin))
+
+        active = [(lane, lane_steps(lane, b)) for lane, b in zip(self.lanes, per_lane) if b]
+        while active:
+            for item in list(active):
+                lane, it = item
+                with lane.context():
+                    try:
+                        next(it)
+                    except StopIteration:
+                        active.remove(item)
+        if use_streams:
+            cur = torch.cuda.current_stream()
+            for lane in self.lanes:
+                if lane.stream is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(lane.stream)
+                    cur.wait_event(ev)
+        for maps, spin, alm, fl in jobs:
+            if fl is not None:
+                alm.mul_(self._fl_full(fl))
+        return [alm for _, _, alm, _ in jobs]
 
     def _fl_full(self, fl):
         """fl[l] expanded to the alm layout (complex128 [nalm])"""
@@ -383,6 +470,53 @@ class DistributedTransform:
             t = torch.from_numpy(full).to(self.device).to(torch.complex128)
             self._ws[key] = t
         return t
+
+
+def make_lanes(ctx, nside, lmax, n=2, group=None):
+    """
+    ``n`` lanes for a CUDA DistributedTransform: lane 0 is the given context and process group on the CALLER's current
+    stream (the one ``ctx`` is set to), every further lane has a library context, stream and world communicator of
+    its own (creating a communicator costs about a second; they are cached per process).
+    """
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+
+    lanes = []
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    for i in range(n):
+        if i == 0:
+            lanes.append(Lane(StagedKernels(ctx, nside, lmax), group, None))
+            continue
+        c = _lib.extra_context(ctx.device, i)
+        st = torch.cuda.Stream(device=ctx.device)
+        c.set_stream(st.cuda_stream)
+        lanes.append(Lane(StagedKernels(c, nside, lmax), _extra_group(i) if multi else group, st))
+    return lanes
+
+
+class ReadyOnce:
+    """
+    "the maps of this spin may be read": waits for an asynchronous reduction, runs ``finish`` ONCE (on the first lane
+    that asks) and makes every other stream that asks later wait for that, too.
+    """
+
+    def __init__(self, work=None, finish=None):
+        self.work, self.finish, self.event = work, finish, None
+
+    def __call__(self):
+        import torch
+
+        if self.work is not None:
+            self.work.wait()  # the current stream waits for the collective
+        if self.event is None:
+            if self.finish is not None:
+                self.finish()
+            self.event = torch.cuda.Event()
+            self.event.record()
+        else:
+            torch.cuda.current_stream().wait_event(self.event)
 
 
 def reduce_maps(maps, group=None):
@@ -423,17 +557,22 @@ def as_torch(arr, device):
     return torch.as_tensor(_CudaView(ptr, arr.shape, arr.dtype.str), device=device)
 
 
-_REDUCE_GROUP = None
+_EXTRA_GROUPS: dict = {}
+
+
+def _extra_group(i: int = 1):
+    """extra world communicators, one per index, created on first use (creating one costs about a second);
+    every rank must ask for them in the same order"""
+    import torch.distributed as dist
+
+    if i not in _EXTRA_GROUPS:
+        _EXTRA_GROUPS[i] = dist.new_group()
+    return _EXTRA_GROUPS[i]
 
 
 def _reduce_group():
-    """one extra world communicator per process, created on first use (creating one costs about a second)"""
-    global _REDUCE_GROUP
-    import torch.distributed as dist
-
-    if _REDUCE_GROUP is None:
-        _REDUCE_GROUP = dist.new_group()
-    return _REDUCE_GROUP
+    """the communicator of lane 1, which also carries the asynchronous spin-2 map reduction"""
+    return _extra_group(1)
 
 
 class DistributedPipeline:
@@ -463,11 +602,17 @@ class DistributedPipeline:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = torch.device("cuda", self.ctx.device)
         self.plan = ShardPlan(mapper.nside, mapper.lmax, self.world)
-        self.kernels = StagedKernels(self.ctx, mapper.nside, mapper.lmax)
-        self.transform = DistributedTransform(self.kernels, self.plan, self.rank, group=group, niter=mapper.niter, device=self.device)
-        # a second communicator for the spin-2 map reduction that overlaps the spin-0 transform
-        # (collectives of one communicator run in issue order)
-        self.reduce_group = _reduce_group() if self.world > 1 and group is None else group
+        # two lanes: the ring FFTs and the all-to-all of one Legendre batch run under the Legendre kernels of another;
+        # lane 1's communicator also carries the asynchronous spin-2 map reduction
+        lanes = make_lanes(self.ctx, mapper.nside, mapper.lmax, 2 if self.world > 1 else 1, group=group)
+        self.kernels = lanes[0].k
+        self.transform = DistributedTransform(self.kernels, self.plan, self.rank, group=group, niter=mapper.niter,
+                                              device=self.device, lanes=lanes)
+        self.reduce_group = lanes[-1].group if self.world > 1 else group
+        # from here on the library works on torch's current stream, so that the mapper's kernels, the copies of `put`
+        # and the transforms are ordered without host synchronisation
+        self.ctx.synchronize()
+        self.kernels.sync_streams()
         self.stacks = {}
         if npos:
             self.stacks[0] = torch.zeros(npos, self.plan.npix, dtype=torch.float64, device=self.device)
@@ -475,15 +620,23 @@ class DistributedPipeline:
             self.stacks[2] = torch.zeros(2 * nshe, self.plan.npix, dtype=torch.float64, device=self.device)
 
     def put(self, spin: int, index: int, m) -> None:
-        """copy partial map ``index`` of the given spin into the device stack"""
-        self.ctx.synchronize()  # whatever stream mapped into m has finished
-        self.kernels.sync_streams()
+        """copy partial map ``index`` of the given spin into the device stack (asynchronous on the library's stream:
+        the caller may reuse or free ``m`` after the next ``synchronize`` of the context, which ``spectra`` does)"""
+        self.kernels.sync_streams()  # the copy is ordered after the kernels that mapped into m
         if hasattr(m, "to_device"):
             m.to_device()
         src = as_torch(m, self.device).reshape(-1, self.plan.npix)
         n = src.shape[0]
         self.stacks[spin][index * n:(index + 1) * n].copy_(src)
-        self.ctx.synchronize()  # the source may be freed by the caller
+        self._pending = True
+
+    def flush(self) -> None:
+        """wait until every ``put`` has landed (the sources may be reused afterwards)"""
+        import torch
+
+        if getattr(self, "_pending", False):
+            torch.cuda.current_stream().synchronize()
+            self._pending = False
 
     def alms(self, spin, finish=None, reduced=False):
         """stack of one spin -> m-distributed alm tensor [rows, nalm] (reduced: already summed over the ranks)"""
@@ -504,18 +657,25 @@ class DistributedPipeline:
 
         import torch.distributed as dist
 
-        parts, work = [], None
-        if 0 in self.stacks:
-            if 2 in self.stacks and self.world > 1:
-                # the spin-2 stack is summed over the ranks on NCCL's stream while the spin-0 maps are transformed
-                self.kernels.sync_streams()
-                work = dist.all_reduce(self.stacks[2], group=self.reduce_group, async_op=True)
-            parts.append(self.alms(0, finish))
-        if 2 in self.stacks:
-            if work is not None:
-                work.wait()
-            parts.append(self.alms(2, finish, reduced=work is not None))
-        alm = torch.cat(parts) if len(parts) > 1 else parts[0]
+        self.kernels.sync_streams()
+        jobs, ready, alms = [], {}, []
+        for spin in (0, 2):
+            if spin not in self.stacks:
+                continue
+            stack = self.stacks[spin]
+            fin = (lambda st=stack, sp=spin: finish(st, sp)) if finish is not None else None
+            work = None
+            if self.world > 1:
+                if spin == 0:
+                    dist.all_reduce(stack, group=self.group)
+                else:  # summed over the ranks on lane 1's communicator while the spin-0 batch is transformed
+                    work = dist.all_reduce(stack, group=self.reduce_group, async_op=True)
+            ready[spin] = ReadyOnce(work, fin)
+            alm = torch.zeros(stack.shape[0], self.plan.nalm, dtype=torch.complex128, device=self.device)
+            alms.append(alm)
+            jobs.append((stack, spin, alm, self.mapper._fl(spin)))
+        self.transform.map2alm_jobs(jobs, ready)
+        alm = torch.cat(alms) if len(alms) > 1 else alms[0]
         n, lmax = alm.shape[0], self.plan.lmax
         cl = torch.zeros(n, n, lmax + 1, dtype=torch.float64, device=self.device)
         # only the m this rank owns contribute (the other entries are zero and need not be read)
