@@ -188,15 +188,18 @@ class Pipeline:
             from heracles_b200.dist import DistributedTransform, ShardPlan, make_lanes
 
             self.plan = ShardPlan(nside, lmax, world)
-            # two lanes: the FFT / all-to-all stages of one Legendre batch run under the Legendre kernels of another;
-            # lane 1's communicator also carries the asynchronous SHE map reduction (collectives of ONE communicator
-            # run in issue order, so it would otherwise queue in front of the spin-0 exchange)
-            self.lanes = make_lanes(self.ctx, nside, lmax, int(os.environ.get("HCU_BENCH_LANES", "2")))
+            # HCU_BENCH_LANES=2: the FFT / all-to-all stages of one Legendre batch are queued under the Legendre kernels of
+            # another (measured: no gain, profiles/r02_lanes_c3_n2.txt; default 1).  The asynchronous SHE map reduction
+            # gets a communicator of its own (collectives of ONE communicator run in issue order, so it would
+            # otherwise queue in front of the spin-0 exchange)
+            self.lanes = make_lanes(self.ctx, nside, lmax, int(os.environ.get("HCU_BENCH_LANES", "1")))
             for lane in self.lanes:
                 lane.k.ctx.set_timing(True)
             self.kernels = self.lanes[0].k
             self.dist = DistributedTransform(self.kernels, self.plan, rank, niter=niter, device=torch.device("cuda"), lanes=self.lanes)
-            self.reduce_group = self.lanes[-1].group
+            from heracles_b200.dist import _reduce_group
+
+            self.reduce_group = self.lanes[-1].group if len(self.lanes) > 1 else _reduce_group()
         self.make_catalogue()
 
     # synthetic catalogue: uniform positions, w ~ U(0.5,1.5), g ~ N(0,0.3)  

@@ -8,6 +8,7 @@ Public surface (mirrors the reference interfaces of this path):
   CudaHealpixMapper            <- heracles.healpy.HealpixMapper
   alm2cl, angular_power_spectra <- heracles.twopoint
   transform                    <- heracles.mapping.transform (batched over maps)
+  dices.region_alms, dices.jackknife_cls <- heracles.dices.jackknife (batched region transforms)
 
 There is no CPU fallback: importing the kernels' library fails loudly if
 ``heracles_b200/lib/libheracles_cuda.so`` has not been built, and creating a
@@ -19,6 +20,7 @@ from .arrays import DeviceArray, update_metadata  # noqa: F401
 from .mapper import CudaHealpixMapper  # noqa: F401
 from .mapping import transform, transform_maps  # noqa: F401
 from .twopoint import alm2cl, alm2lmax, angular_power_spectra  # noqa: F401
+from . import dices  # noqa: F401,E402
 
 __all__ = [
     "CudaHealpixMapper",
@@ -28,6 +30,7 @@ __all__ = [
     "alm2cl",
     "alm2lmax",
     "angular_power_spectra",
+    "dices",
     "get_context",
     "load",
     "update_metadata",

@@ -66,6 +66,7 @@ SIGNATURES = {
     "hcu_set_timing": (c_int, [c_vp, c_int]),
     "hcu_set_weights_mode": (c_int, [c_vp, c_int]),
     "hcu_multiply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64]),
+    "hcu_region_select": (c_int, [c_vp, c_vp, c_vp, c_vp, c_dbl, c_i64]),
     "hcu_last_sht_timing": (c_int, [c_vp, ctypes.POINTER(ctypes.c_float * 4)]),
     "hcu_last_sht_work": (c_int, [c_vp, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),
     "hcu_measure_fp64_peak": (c_int, [c_vp, ctypes.POINTER(c_dbl)]),

@@ -44,21 +44,27 @@ class _ManagedBuffer:
 
 
 def update_metadata(array, *sources, **metadata):
-    """same contract as heracles.core.update_metadata (core.py:102-122)"""
+    """same contract as heracles.core.update_metadata (core.py:100-122): ``sources`` are objects with a ``metadata``
+    mapping (catalogues, fields.py:312); arrays are accepted too and contribute their ``dtype.metadata``"""
     md = {}
     if array.dtype.metadata is not None:
         md.update(array.dtype.metadata)
     for source in sources:
-        if source.dtype.metadata is not None:
-            md.update(source.dtype.metadata)
+        smd = getattr(source, "metadata", None)
+        if smd is None and isinstance(source, np.ndarray):
+            smd = source.dtype.metadata
+        if smd:
+            md.update(smd)
     md.update(metadata)
-    if not md:
-        return
     if array.dtype.fields is not None:
         dt = array.dtype.fields
     else:
         dt = array.dtype.str
-    array.dtype = np.dtype(dt, metadata=md)
+    dt = np.dtype(dt, metadata=md)
+    if not np.can_cast(dt, array.dtype, casting="no"):
+        msg = "array with unsupported dtype"
+        raise ValueError(msg)
+    array.dtype = dt
 
 
 class DeviceArray(np.ndarray):

@@ -307,6 +307,12 @@ __global__ void axpy_kernel(double *y, const double *x, double a, i64 n) {
   i64 s = (i64)gridDim.x * blockDim.x;
   for (; i < n; i += s) y[i] += a * x[i];
 }
+// out = (region map == k) ? in : 0 -- the jackknife region mask of DICES (heracles/dices/jackknife.py: _get_region_maps)
+__global__ void region_select_kernel(double *out, const double *in, const double *jk, double k, i64 n) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 s = (i64)gridDim.x * blockDim.x;
+  for (; i < n; i += s) out[i] = (jk[i] == k) ? in[i] : 0.0;
+}
 __global__ void mul_kernel(double *out, const double *a, const double *b, i64 n) {
   i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   i64 s = (i64)gridDim.x * blockDim.x;
@@ -502,6 +508,14 @@ extern "C" int hcu_reorder(hcu_ctx *ctx, int64_t nside, const double *in, double
   HCU_ARG(nside >= 1 && (nside & (nside - 1)) == 0, "nside must be a power of two");
   const i64 npix = 12 * nside * nside;
   reorder_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(nside, ilog2_host(nside), in, out, to_nest);
+  HCU_LAUNCH_CHECK(ctx);
+  return HCU_OK;
+}
+
+extern "C" int hcu_region_select(hcu_ctx *ctx, double *out, const double *in, const double *jk_map, double region, int64_t n) {
+  HCU_ARG(ctx && out && in && jk_map && n >= 0, "hcu_region_select");
+  if (n == 0) return HCU_OK;
+  region_select_kernel<<<ew_blocks(ctx, n), 256, 0, ctx->stream>>>(out, in, jk_map, region, n);
   HCU_LAUNCH_CHECK(ctx);
   return HCU_OK;
 }

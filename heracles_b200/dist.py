@@ -592,7 +592,7 @@ class DistributedPipeline:
     (E, B) per spin-2 field; only the upper triangle j >= i is filled).
     """
 
-    def __init__(self, mapper, npos: int = 0, nshe: int = 0, group=None):
+    def __init__(self, mapper, npos: int = 0, nshe: int = 0, group=None, lanes: int = 1):
         import torch
         import torch.distributed as dist
 
@@ -602,13 +602,16 @@ class DistributedPipeline:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = torch.device("cuda", self.ctx.device)
         self.plan = ShardPlan(mapper.nside, mapper.lmax, self.world)
-        # two lanes: the ring FFTs and the all-to-all of one Legendre batch run under the Legendre kernels of another;
-        # lane 1's communicator also carries the asynchronous spin-2 map reduction
-        lanes = make_lanes(self.ctx, mapper.nside, mapper.lmax, 2 if self.world > 1 else 1, group=group)
+        # lanes = 2: the ring FFTs and the all-to-all of one Legendre batch are queued under the Legendre kernels of
+        # another.  Measured (profiles/r02_lanes_c3_n2.txt): no gain -- a Legendre CTA takes a whole SM (all registers,
+        # 205 KB of shared memory), so the second lane's kernels time-slice the SMs instead of sharing them; default 1.
+        lanes = make_lanes(self.ctx, mapper.nside, mapper.lmax, lanes if self.world > 1 else 1, group=group)
         self.kernels = lanes[0].k
         self.transform = DistributedTransform(self.kernels, self.plan, self.rank, group=group, niter=mapper.niter,
                                               device=self.device, lanes=lanes)
-        self.reduce_group = lanes[-1].group if self.world > 1 else group
+        # a communicator of its own for the asynchronous spin-2 map reduction (collectives of ONE communicator run in
+        # issue order, so it would otherwise queue in front of the spin-0 exchange)
+        self.reduce_group = (lanes[-1].group if len(lanes) > 1 else _reduce_group()) if self.world > 1 and group is None else group
         # from here on the library works on torch's current stream, so that the mapper's kernels, the copies of `put`
         # and the transforms are ordered without host synchronisation
         self.ctx.synchronize()

@@ -122,6 +122,9 @@ int hcu_divide(hcu_ctx *ctx, double *x, int64_t n, double a);         /* x /= a 
 int hcu_axpy(hcu_ctx *ctx, double *y, const double *x, double a, int64_t n); /* y += a x */
 int hcu_add_scalar(hcu_ctx *ctx, double *x, int64_t n, double a);     /* x += a        */
 int hcu_multiply(hcu_ctx *ctx, double *out, const double *a, const double *b, int64_t n); /* out = a b (masks) */
+/* out = (jk_map == region) ? in : 0: the jackknife region maps of DICES (heracles/dices/jackknife.py,
+ * _get_region_maps: deepcopy + `_map *= (jk_map == float(jk))` per region) without leaving the device */
+int hcu_region_select(hcu_ctx *ctx, double *out, const double *in, const double *jk_map, double region, int64_t n);
 
 /* hp.reorder(map, r2n / n2r): RING <-> NEST order of a whole map (out of place; device or managed memory).
  * The transform works on RING maps; a mapper configured for NEST maps reorders before hcu_map2alm. */
