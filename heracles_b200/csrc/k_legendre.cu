@@ -50,6 +50,14 @@ constexpr int NT = 32 * NW;
 constexpr int FLS = 34;      // column stride of a flush tile (32 l + 2: conflict free)
 
 
+// st.shared.v2.f64 of (a, b) when ok, of zeros otherwise
+__device__ __forceinline__ void sts2_pred1(unsigned addr, double a, double b, int ok) {
+  asm volatile(
+      "{\n .reg .pred q;\n setp.ne.s32 q, %3, 0;\n @q st.shared.v2.f64 [%0], {%1, %2};\n"
+      " @!q st.shared.v2.f64 [%0], {%4, %4};\n}" ::"r"(addr),
+      "d"(a), "d"(b), "r"(ok), "d"(0.0));
+}
+
 template <int SPIN>
 struct Rec {
   static constexpr int NJ = SPIN == 0 ? 1 : 2;
@@ -72,20 +80,24 @@ struct Rec {
   __device__ __forceinline__ bool sub_live() const {
     return __any_sync(0xffffffffu, alive && (sp.e == 0 || (SPIN != 0 && sm.e == 0)));
   }
-  // four recursion steps s..s+3 of the current sub-chunk (s multiple of 4) and their stores
+  // four recursion steps s..s+3 of the current sub-chunk (s multiple of 4) and their stores.
+  // Values that are not representable yet (extended exponent e < 0) are stored as zeros by a predicated second
+  // store (st.shared of RZ) instead of being masked: 16 LOP3 and as many register moves less per step group.
   __device__ __forceinline__ void step4(double *tile, const double *cf, int ring, int pb, int s) {
     double vp[4], vm[4];
+    double2 c2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c2[u] = reinterpret_cast<const double2 *>(cf)[s + u];  // all four loads before the chain
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const double2 c2 = reinterpret_cast<const double2 *>(cf)[s + u];
-      vp[u] = mask_d(sp.cur, mp);
+      vp[u] = sp.cur;
       if (SPIN == 0) {
-        const double nw = fma(c2.x * x, sp.cur, -sp.prev);
+        const double nw = fma(c2[u].x * x, sp.cur, -sp.prev);
         sp.prev = sp.cur;
         sp.cur = nw;
       } else {
-        vm[u] = mask_d(sm.cur, mm);
-        const double ap = fma(c2.x, x, c2.y), am = fma(c2.x, x, -c2.y);
+        vm[u] = sm.cur;
+        const double ap = fma(c2[u].x, x, c2[u].y), am = fma(c2[u].x, x, -c2[u].y);
         const double np = fma(ap, sp.cur, -sp.prev);
         const double nm = fma(am, sm.cur, -sm.prev);
         sp.prev = sp.cur; sp.cur = np;
@@ -93,23 +105,26 @@ struct Rec {
       }
     }
     // steps s, s+2 have parity pb; s+1, s+3 parity 1-pb; l index within the parity s/2, s/2+1
-    const int o = o4[s >> 2];
-    *reinterpret_cast<double2 *>(tile + pb * 256 + o) = make_double2(vp[0], vp[2]);
-    *reinterpret_cast<double2 *>(tile + (1 - pb) * 256 + o) = make_double2(vp[1], vp[3]);
+    const unsigned o = (unsigned)__cvta_generic_to_shared(tile) + 8u * (unsigned)o4[s >> 2];
+    const int okp = mp != 0ull, okm = mm != 0ull;
+    sts2_pred1(o + 2048u * pb, vp[0], vp[2], okp);
+    sts2_pred1(o + 2048u * (1 - pb), vp[1], vp[3], okp);
     if (SPIN != 0) {
-      *reinterpret_cast<double2 *>(tile + (2 + pb) * 256 + o) = make_double2(vm[0], vm[2]);
-      *reinterpret_cast<double2 *>(tile + (3 - pb) * 256 + o) = make_double2(vm[1], vm[3]);
+      sts2_pred1(o + 2048u * (2 + pb), vm[0], vm[2], okm);
+      sts2_pred1(o + 2048u * (3 - pb), vm[1], vm[3], okm);
     }
   }
-  // extended-exponent bookkeeping, once per sub-chunk (values grow by far less than 2^400 in 16 steps)
+  // extended-exponent bookkeeping, once per sub-chunk (values grow by far less than 2^400 in 16 steps);
+  // the magnitude test reads the exponent fields on the integer pipe (a DSETP would queue behind the DMMAs)
   __device__ __forceinline__ void end_sub() {
     if (__any_sync(0xffffffffu, sp.e < 0 || (SPIN != 0 && sm.e < 0))) {
-      if (sp.e < 0 && fmax(fabs(sp.cur), fabs(sp.prev)) >= TWO_P200) {
+      if (sp.e < 0 && max(__double2hiint(sp.cur) & 0x7ff00000, __double2hiint(sp.prev) & 0x7ff00000) >= 0x4c700000) {
         sp.cur *= TWO_M400;
         sp.prev *= TWO_M400;
         sp.e += SCALE_STEP;
       }
-      if (SPIN != 0 && sm.e < 0 && fmax(fabs(sm.cur), fabs(sm.prev)) >= TWO_P200) {
+      if (SPIN != 0 && sm.e < 0 &&
+          max(__double2hiint(sm.cur) & 0x7ff00000, __double2hiint(sm.prev) & 0x7ff00000) >= 0x4c700000) {
         sm.cur *= TWO_M400;
         sm.prev *= TWO_M400;
         sm.e += SCALE_STEP;
@@ -755,7 +770,7 @@ int hcu_legendre2_synthesis(hcu_ctx *ctx, void *args, const i64 *rp_bounds, int 
 // analysis passes + one synthesis pass): a launch costs  a + b * columns  with b at the FP64 pipe's peak for BOTH
 // generations and a latency-bound fixed part a (recursion, tile hand-over) that does not depend on the columns:
 //     spin 0   <= 4 maps: gen 1;   5..8 maps: gen 2 (75.8 + 38.6 ms against 93.5 + 45.1);   9..12 maps: gen 1 (3 n-blocks)
-//     spin 2   gen 1 (4 fields 159 + 76.7 ms against 160.5 + 84.5)
+//     spin 2   gen 1 (4 fields 159 + 76.7 ms against 160.5 + 84.5); <= 2 fields: gen 2 synthesis (one n-block)
 // HCU_LEGENDRE_GEN = 1 | 2 forces one generation (A/B timing, tests); HCU_LEGENDRE_NW = 12 | 16 are the warps per CTA
 // of the second-generation analysis kernel (8: experimental 16-component analysis-only batches).
 static int legendre_gen_env() {
@@ -774,11 +789,14 @@ static int legendre_nw() {
   }
   return nw;
 }
-static int legendre_gen(int spin, int ncomp) {
+static int legendre_gen(int spin, int ncomp, bool synthesis) {
   const int forced = legendre_gen_env();
   if (forced == 1) return 1;
   if (forced == 2) return ncomp <= 8 || legendre_nw() == 8 ? 2 : 1;
-  return (spin == 0 && ncomp >= 5 && ncomp <= 8) ? 2 : 1;
+  if (spin == 0) return (ncomp >= 5 && ncomp <= 8) ? 2 : 1;
+  // spin 2: the second-generation synthesis has a one-n-block variant for <= 2 fields (half the DMMAs of the
+  // first generation's fixed (+2a | -2a) two-block layout)
+  return (synthesis && ncomp <= 4) ? 2 : 1;
 }
 
 // components one Legendre launch takes: 12 spin-0 maps or 4 spin-2 fields (Q, U rows);
@@ -826,7 +844,7 @@ int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
   a.fl = fl_dev;
   a.alm = alm;
   a.work = ctx->work_counters;
-  if (legendre_gen(spin, ncomp) == 2) return hcu_legendre2_analysis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
+  if (legendre_gen(spin, ncomp, false) == 2) return hcu_legendre2_analysis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
   // 8 output columns per n-block: 4 spin-0 maps, or 2 spin-2 fields (4 Q/U rows)
   const int ncolblk = (ncomp + 3) / 4;
   if (spin == 0) {
@@ -850,7 +868,7 @@ int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
   fill_args(a, g, c, lmax, ncomp, mlist_dev, nm, nblk, rp_bounds);
   a.alm = alm;
   a.phase_out = phase;
-  if (legendre_gen(spin, ncomp) == 2) return hcu_legendre2_synthesis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
+  if (legendre_gen(spin, ncomp, true) == 2) return hcu_legendre2_synthesis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
   if (spin == 0) {
     switch ((ncomp + 3) / 4) {
       case 1: return launch_synthesis<0, 1>(ctx, a);

@@ -514,7 +514,7 @@ struct S2Cfg {
   static constexpr int R = NW * RW;
   static constexpr int NT = 32 * NW;
   static constexpr int C = 8 * NBLK;
-  static constexpr int NROW = SPIN == 0 ? 4 * NBLK : 8;   // alm rows (components) staged per l
+  static constexpr int NROW = 4 * NBLK;                   // alm rows (components) staged per l
   static constexpr int BSTR = 20;                         // row stride of the a_lm tile: 4 (mod 16), >= 2 NROW
   static constexpr int TILE = 2 * 256;
   static constexpr int TPAD = 2;                          // doubles between the two t-blocks: rows r and 16 + r of a tile
@@ -523,7 +523,6 @@ struct S2Cfg {
   static constexpr int BT = 2 * TSTR;                     // one a_lm tile: [t][16][BSTR]
   static constexpr int WARP = 2 * TILE + 2 * SL * 2 + 2 * BT;
   static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(NW * WARP);
-  static_assert(SPIN == 0 || NBLK == 2, "spin 2 synthesis uses the (+2a | -2a) two-block column layout");
   static_assert(2 * NROW <= BSTR, "a_lm row does not fit");
 };
 
@@ -602,17 +601,23 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_synthesis2_kernel(LegArgs
         *reinterpret_cast<double2 *>(row + 2 * i) = make_double2(v.x * sc, v.y * sc);
       }
     } else {
-      double2 E[4], B[4];
+      // columns: [ +2a of the NF fields | sg -2a of the NF fields ], sg = (-1)^(l+m): with the sign of the southern
+      // ring folded into the -2a half, ONE operand tile serves both Wigner functions (the lambda^{-2} blocks flip
+      // the sign of their A fragment instead) and two fields fill exactly one n-block
+      constexpr int NF = 2 * NBLK;
+      const double sg = ((st.pb ^ (lane & 1)) ? -1.0 : 1.0) * sc;
+      double2 E[NF], B[NF];
 #pragma unroll
-      for (int f = 0; f < 4; ++f) {
+      for (int f = 0; f < NF; ++f) {
         E[f] = *reinterpret_cast<double2 *>(row + 4 * f);
         B[f] = *reinterpret_cast<double2 *>(row + 4 * f + 2);
         if (2 * f >= a.ncomp) E[f] = B[f] = make_double2(0., 0.);
       }
 #pragma unroll
-      for (int f = 0; f < 4; ++f) {
+      for (int f = 0; f < NF; ++f) {
+        // +2a = -(E + iB), -2a = -(E - iB)
         *reinterpret_cast<double2 *>(row + 2 * f) = make_double2(-(E[f].x - B[f].y) * sc, -(E[f].y + B[f].x) * sc);
-        *reinterpret_cast<double2 *>(row + 8 + 2 * f) = make_double2(-(E[f].x + B[f].y) * sc, -(E[f].y - B[f].x) * sc);
+        *reinterpret_cast<double2 *>(row + 2 * NF + 2 * f) = make_double2(-(E[f].x + B[f].y) * sg, -(E[f].y - B[f].x) * sg);
       }
     }
   };
@@ -676,18 +681,13 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_synthesis2_kernel(LegArgs
 #pragma unroll
               for (int nb = 0; nb < NBLK; ++nb) dmma(acc[t][mb][nb][0], acc[t][mb][nb][1], av, bfr[nb]);
             } else {
-              // v-blocks 0, 1: lambda^{+2} of ring pairs 0..7, 8..15; 2, 3: lambda^{-2}
-              //   j = 0:  acc[mb][0] = P_N = sum lam+ (+2a)       acc[mb][1] = M_S = sum sg lam+ (-2a)
-              //   j = 1:  acc[mb][0] = P_S = sum sg lam- (+2a)    acc[mb][1] = M_N = sum lam- (-2a)
-              // sg = (-1)^(l+m): the sign goes onto the A fragment (integer pipe)
-              const double avs = xor_hi(av, t ? sflip1 : sflip0);
-              if (mb < 2) {
-                dmma(acc[0][mb][0][0], acc[0][mb][0][1], av, bfr[0]);
-                dmma(acc[0][mb][1][0], acc[0][mb][1][1], avs, bfr[1]);
-              } else {
-                dmma(acc[0][mb][0][0], acc[0][mb][0][1], avs, bfr[0]);
-                dmma(acc[0][mb][1][0], acc[0][mb][1][1], av, bfr[1]);
-              }
+              // v-blocks 0, 1: lambda^{+2} of ring pairs 0..7, 8..15; 2, 3: lambda^{-2}; columns [ +2a | sg -2a ]:
+              //   j = 0:  acc[mb][+] = P_N = sum lam+ (+2a)          acc[mb][-] = M_S = sum lam+ sg (-2a)
+              //   j = 1:  acc[mb][+] = P_S = sum (sg lam-) (+2a)     acc[mb][-] = M_N = sum (sg lam-) sg (-2a)
+              // sg = (-1)^(l+m) goes onto the A fragment of the lambda^{-2} blocks (integer pipe)
+              const double af = mb < 2 ? av : xor_hi(av, t ? sflip1 : sflip0);
+#pragma unroll
+              for (int nb = 0; nb < NBLK; ++nb) dmma(acc[0][mb][nb][0], acc[0][mb][nb][1], af, bfr[nb]);
             }
           }
           if (th == 0) chore(0);
@@ -723,22 +723,41 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_synthesis2_kernel(LegArgs
       }
     }
   } else {
-    // ring pair rb*8 + fb (rb = 0, 1): lambda^{+2} sums in v-block rb, lambda^{-2} sums in v-block 2 + rb; field fa
-    const int f = fa;
+    // ring pair rb*8 + fb (rb = 0, 1): lambda^{+2} sums in v-block rb, lambda^{-2} sums in v-block 2 + rb
 #pragma unroll
     for (int rb = 0; rb < 2; ++rb) {
       const int r = warp * K::RW + rb * 8 + fb;
-      if (r >= st.nrows || 2 * f >= a.ncomp) continue;
-      const double PrN = acc[0][rb][0][0], PiN = acc[0][rb][0][1];
-      const double MrS = acc[0][rb][1][0], MiS = acc[0][rb][1][1];
-      const double PrS = acc[0][2 + rb][0][0], PiS = acc[0][2 + rb][0][1];
-      const double MrN = acc[0][2 + rb][1][0], MiN = acc[0][2 + rb][1][1];
-      double *d = dst + ((i64)r * a.ncomp + 2 * f) * 4;
-      // Q = (P + M)/2 ; U = (P - M)/(2i)
-      *reinterpret_cast<double4 *>(d) =
-          make_double4(0.5 * (PrN + MrN), 0.5 * (PiN + MiN), 0.5 * (PrS + MrS), 0.5 * (PiS + MiS));
-      *reinterpret_cast<double4 *>(d + 4) =
-          make_double4(0.5 * (PiN - MiN), -0.5 * (PrN - MrN), 0.5 * (PiS - MiS), -0.5 * (PrS - MrS));
+      if constexpr (NBLK == 2) {
+        // columns 2 fa, 2 fa + 1 of block 0 (+2a) and of block 1 (-2a): field fa
+        const int f = fa;
+        if (r >= st.nrows || 2 * f >= a.ncomp) continue;
+        const double PrN = acc[0][rb][0][0], PiN = acc[0][rb][0][1];
+        const double MrS = acc[0][rb][1][0], MiS = acc[0][rb][1][1];
+        const double PrS = acc[0][2 + rb][0][0], PiS = acc[0][2 + rb][0][1];
+        const double MrN = acc[0][2 + rb][1][0], MiN = acc[0][2 + rb][1][1];
+        double *d = dst + ((i64)r * a.ncomp + 2 * f) * 4;
+        // Q = (P + M)/2 ; U = (P - M)/(2i)
+        *reinterpret_cast<double4 *>(d) =
+            make_double4(0.5 * (PrN + MrN), 0.5 * (PiN + MiN), 0.5 * (PrS + MrS), 0.5 * (PiS + MiS));
+        *reinterpret_cast<double4 *>(d + 4) =
+            make_double4(0.5 * (PiN - MiN), -0.5 * (PrN - MrN), 0.5 * (PiS - MiS), -0.5 * (PrS - MrS));
+      } else {
+        // one n-block: lanes fa = 0, 1 hold the +2a columns of fields 0, 1 (P_N in v-block rb, P_S in 2 + rb), lanes
+        // fa = 2, 3 the -2a columns (M_S, M_N); partners (fa ^ 2) swap, the P lane writes the Q row, the M lane the U row
+        const double x0r = acc[0][rb][0][0], x0i = acc[0][rb][0][1];
+        const double x1r = acc[0][2 + rb][0][0], x1i = acc[0][2 + rb][0][1];
+        const double y0r = __shfl_xor_sync(0xffffffffu, x0r, 2), y0i = __shfl_xor_sync(0xffffffffu, x0i, 2);
+        const double y1r = __shfl_xor_sync(0xffffffffu, x1r, 2), y1i = __shfl_xor_sync(0xffffffffu, x1i, 2);
+        const int f = fa & 1;
+        if (r >= st.nrows || 2 * f >= a.ncomp) continue;
+        double *d = dst + ((i64)r * a.ncomp + 2 * f) * 4;
+        if (fa < 2) {  // P lane: P_N = x0, P_S = x1, M_S = y0, M_N = y1
+          *reinterpret_cast<double4 *>(d) = make_double4(0.5 * (x0r + y1r), 0.5 * (x0i + y1i), 0.5 * (x1r + y0r), 0.5 * (x1i + y0i));
+        } else {       // M lane: M_S = x0, M_N = x1, P_N = y0, P_S = y1
+          *reinterpret_cast<double4 *>(d + 4) =
+              make_double4(0.5 * (y0i - x1i), -0.5 * (y0r - x1r), 0.5 * (y1i - x0i), -0.5 * (y1r - x0r));
+        }
+      }
     }
   }
 }
@@ -800,5 +819,5 @@ int hcu_legendre2_synthesis(hcu_ctx *ctx, void *args, const i64 *rp_bounds, int 
     const int nblk = (ncomp + 3) / 4 <= 1 ? 1 : 2;
     return nblk == 1 ? launch_synthesis2<0, 12, 1>(ctx, a, rp_bounds) : launch_synthesis2<0, 12, 2>(ctx, a, rp_bounds);
   }
-  return launch_synthesis2<2, 12, 2>(ctx, a, rp_bounds);
+  return ncomp <= 4 ? launch_synthesis2<2, 12, 1>(ctx, a, rp_bounds) : launch_synthesis2<2, 12, 2>(ctx, a, rp_bounds);
 }
