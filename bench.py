@@ -261,6 +261,42 @@ class Pipeline:
                 g2 = g0 + 2 * off + rows * 8 if self.cfg["she"] else None
                 self.check(lib.hcu_map_page(h, nside, 0, lon0 + off, lat0 + off, w0 + off, g1, g2, rows, pos_ptr, she_ptr, npix, None))
 
+    def tile_sorted_rate(self, reps=3):
+        """
+        SURVEY 8(d): the scatter rate on a TILE-SORTED catalogue -- the rows of every page of bin 0 ordered by their
+        nside = 64 NEST parent pixel, the locality a survey catalogue has in file order -- next to the uniform one the
+        timed step uses.  Returns GB/s of algorithmic bytes (88 B / row POS + SHE, 40 B / row POS only).
+        """
+        torch = self.torch
+        c = self.cat[0]
+        rows, n = self.page_rows, self.pool * self.page_rows
+        ipix = torch.empty(n, dtype=torch.int64, device="cuda")
+        self.check(self.lib.hcu_ang2pix(self.h, 64, 1, c["lon"].data_ptr(), c["lat"].data_ptr(), n, ipix.data_ptr()))
+        order = torch.argsort(ipix.view(self.pool, rows), dim=1)  # sorted inside every page
+        lon = torch.gather(c["lon"].view(self.pool, rows), 1, order).contiguous()
+        lat = torch.gather(c["lat"].view(self.pool, rows), 1, order).contiguous()
+        w = torch.gather(c["w"].view(self.pool, rows), 1, order).contiguous()
+        g = torch.gather(c["g"], 2, order[:, None, :].expand(-1, 2, -1)).contiguous() if self.cfg["she"] else None
+        del ipix, order
+        npix, nside = self.npix, self.cfg["nside"]
+        pos, she = self.maps[0], (self.maps[self.nbins:self.nbins + 2] if self.cfg["she"] else None)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = None
+        with torch.cuda.stream(self.stream):
+            for _ in range(reps):
+                ev0.record()
+                for p in range(self.pool):
+                    off = p * rows * 8
+                    self.check(self.lib.hcu_map_page(self.h, nside, 0, lon.data_ptr() + off, lat.data_ptr() + off, w.data_ptr() + off,
+                                                     g.data_ptr() + 2 * off if g is not None else None,
+                                                     g.data_ptr() + 2 * off + rows * 8 if g is not None else None, rows,
+                                                     pos.data_ptr(), she.data_ptr() if she is not None else None, npix, None))
+                ev1.record()
+                ev1.synchronize()
+                ms = ev0.elapsed_time(ev1)
+                best = ms if best is None else min(best, ms)
+        return n * (88 if self.cfg["she"] else 40) / (best * 1e-3) / 1e9
+
     def stage_normalise(self, scale=True, shift=True):
         """scale: pos /= nbar, she /= wbar (linear: may precede the sum over ranks); shift: pos -= vis (once, after it)"""
         lib, h, npix = self.lib, self.h, self.npix
@@ -960,9 +996,12 @@ def main():
             "flops": "the executed cells of the analysis passes (same geometry, same skipping) x SURVEY 8(d) per-cell figures",
             "traffic": traffic.get(f"legendre_synthesis_{cfg_name.lower()}"), "share_of_step": stats["leg_syn_ms"] / total_ms,
         }
+    sorted_gbs = pipe.tile_sorted_rate() if pipe.cat is not None else None
     roofline_map = {
         "kernel": "map_page_kernel", "bound": "hbm", "achieved": map_gbs, "peak": hbm_peak, "unit": "GB/s",
         "frac": map_gbs / hbm_peak, "input": "uniform random positions (no locality inside a page)",
+        "tile_sorted": {"achieved": sorted_gbs, "frac": sorted_gbs / hbm_peak if sorted_gbs else None,
+                        "input": "the same rows ordered by their nside-64 NEST parent pixel inside every page (SURVEY 8(d))"},
         "traffic": traffic.get("map_page_1e6_rows"), "traffic_unit": "bytes per 1e6-row POS+SHE launch",
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
         "share_of_step": stats["map_ms"] / total_ms,

@@ -64,6 +64,7 @@ SIGNATURES = {
     "hcu_map_page": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "hcu_reorder": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int]),
     "hcu_set_timing": (c_int, [c_vp, c_int]),
+    "hcu_set_start_table": (c_int, [c_vp, c_int]),
     "hcu_set_weights_mode": (c_int, [c_vp, c_int]),
     "hcu_multiply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64]),
     "hcu_region_select": (c_int, [c_vp, c_vp, c_vp, c_vp, c_dbl, c_i64]),

@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <thread>
 
+#include <stdlib.h>
+
 #include "hcu_common.cuh"
 
 int hcu_mul(hcu_ctx *ctx, double *out, const double *a, const double *b, i64 n);
@@ -68,6 +70,10 @@ extern "C" int hcu_create(int device, hcu_ctx **out) {
   HCU_CUDA(cudaMalloc(&ctx->work_counters, 2 * sizeof(double)));
   HCU_CUDA(cudaMemset(ctx->work_counters, 0, 2 * sizeof(double)));
   for (int i = 0; i < 6; ++i) HCU_CUDA(cudaEventCreate(&ctx->ev[i]));
+  {
+    const char *e = getenv("HCU_START_TABLE");  // 0: walk the dead zone in every pass (A/B timing)
+    if (e && e[0] == '0') ctx->use_start_table = false;
+  }
   *out = ctx;
   return HCU_OK;
 }
@@ -106,6 +112,10 @@ extern "C" int hcu_destroy(hcu_ctx *ctx) {
     cudaFree(kv.second.sh);
     if (kv.second.bfilt) cudaFree(kv.second.bfilt);
     if (kv.second.bfilt_off) cudaFree(kv.second.bfilt_off);
+  }
+  for (auto &kv : ctx->start) {
+    if (kv.second.sub) cudaFree(kv.second.sub);
+    if (kv.second.state) cudaFree(kv.second.state);
   }
   for (auto &kv : ctx->coef) {
     cudaFree(kv.second.tab);
@@ -570,6 +580,35 @@ int hcu_get_coef(hcu_ctx *ctx, int lmax, int spin, hcu_coef **out) {
   HCU_CHECK(hcu_build_coef(ctx, &c));
   ctx->coef[key] = c;
   *out = &ctx->coef[key];
+  return HCU_OK;
+}
+
+int hcu_get_start(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, hcu_start **out) {
+  *out = nullptr;
+  if (!ctx->use_start_table) return HCU_OK;
+  auto key = std::make_pair(g->nside, std::make_pair(c->lmax, c->spin));
+  auto it = ctx->start.find(key);
+  if (it == ctx->start.end()) {
+    hcu_start t;
+    // 20 bytes per (m, ring pair, chain): 3.8 GB for spin 0 + 2 at nside 4096 / lmax 8192.  Built only when it leaves
+    // at least 3/4 of the free memory alone; otherwise (nside 8192) the kernels walk the dead zone as before
+    const size_t n = (size_t)(c->lmax + 1) * g->nrp * (c->spin == 0 ? 1 : 2);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (n * 20 < free_b / 4 && hcu_build_start(ctx, g, c, &t) != HCU_OK) {
+      cudaGetLastError();
+      t = hcu_start();
+    }
+    ctx->start[key] = t;
+    it = ctx->start.find(key);
+  }
+  if (it->second.sub) *out = &it->second;
+  return HCU_OK;
+}
+
+extern "C" int hcu_set_start_table(hcu_ctx *ctx, int enabled) {
+  HCU_ARG(ctx, "ctx");
+  ctx->use_start_table = enabled != 0;
   return HCU_OK;
 }
 

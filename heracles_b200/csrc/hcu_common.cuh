@@ -90,6 +90,13 @@ struct hcu_coef {
   double *cm = nullptr;    // [2 (lmax+1)] start-value normalisation
 };
 
+// per-(nside, lmax, spin) start states of the Legendre recursions: the dead zone l0 <= l < l_start(m, theta), in which
+// lambda_lm is below 2^-200 and contributes nothing, is walked ONCE when the table is built instead of in every pass
+struct hcu_start {
+  int *sub = nullptr;        // [m][ring pair][NJ]: first sub-chunk (16 l, counted from l0) that starts representable; INT_MAX: never
+  double2 *state = nullptr;  // [m][ring pair][NJ]: (prev, cur) of the scaled recursion at the start of that sub-chunk
+};
+
 struct hcu_stage_slot {
   double *host = nullptr; // pinned
   double *dev = nullptr;
@@ -117,6 +124,8 @@ struct hcu_ctx {
   // tables
   std::map<i64, hcu_geom> geom;
   std::map<std::pair<int, int>, hcu_coef> coef;
+  std::map<std::pair<i64, std::pair<int, int>>, hcu_start> start;  // key (nside, (lmax, spin))
+  bool use_start_table = true;
   std::map<i64, cufftHandle> belt_plan, belt_plan_inv;
   // timing
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -129,6 +138,9 @@ struct hcu_ctx {
 int hcu_ws_reserve(hcu_ctx *ctx, hcu_buffer *b, size_t bytes);
 int hcu_get_geom(hcu_ctx *ctx, i64 nside, hcu_geom **out);
 int hcu_get_coef(hcu_ctx *ctx, int lmax, int spin, hcu_coef **out);
+// start-state table for (geometry, coefficients); *out = nullptr when disabled or when it does not fit in memory
+int hcu_get_start(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, hcu_start **out);
+int hcu_build_start(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, hcu_start *t);
 
 // kernels' host launchers (defined in the k_*.cu files)
 int hcu_launch_map_values(hcu_ctx *ctx, i64 nside, int scheme, const double *lon,
@@ -144,6 +156,7 @@ int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
                          const hcu_ptrs &maps);
 int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c);
 int hcu_legendre_batch(int spin);  // components one Legendre launch can take: 12 (spin 0), 8 (spin 2)
+// (both Legendre launchers look the start-state table up themselves)
 int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
                           int spin, int ncomp, const double *phase,
                           const int32_t *mlist_dev, int nm, int nblk, const i64 *rp_bounds,

@@ -66,6 +66,8 @@ struct Rec {
   double x;
   unsigned long long mp, mm;  // store masks: all ones when the value is representable (e == 0)
   bool alive;
+  int ssp, ssm;               // sub-chunk at whose start the chain is first representable (start-state table; 0 without)
+  i64 st_idx;                 // this lane's entry of the start-state table
   int o4[4];                  // swizzled store offsets of the four step groups of a sub-chunk (lane constant)
   __device__ __forceinline__ void init_offsets(int ring) {
 #pragma unroll
@@ -76,9 +78,26 @@ struct Rec {
     mp = (sp.e == 0) ? ~0ull : 0ull;
     mm = (sm.e == 0) ? ~0ull : 0ull;
   }
-  // is anything of the sub-chunk about to be produced representable in this warp?
-  __device__ __forceinline__ bool sub_live() const {
-    return __any_sync(0xffffffffu, alive && (sp.e == 0 || (SPIN != 0 && sm.e == 0)));
+  // is anything of sub-chunk s, which is about to be produced, representable in this warp?
+  __device__ __forceinline__ bool sub_live(int s) const {
+    return __any_sync(0xffffffffu, alive && ((sp.e == 0 && ssp <= s) || (SPIN != 0 && sm.e == 0 && ssm <= s)));
+  }
+  // chains whose dead zone ends at sub-chunk s pick up their state from the table (hcu_start): until then they carry
+  // zeros, exactly what the extended-exponent masks produced while the dead zone was still walked
+  __device__ __forceinline__ void maybe_start(const LegArgs &a, int s) {
+    if (a.st_state == nullptr || !alive) return;
+    if (ssp == s) {
+      const double2 v = a.st_state[st_idx];
+      sp.prev = v.x;
+      sp.cur = v.y;
+      sp.e = 0;
+    }
+    if (SPIN != 0 && ssm == s) {
+      const double2 v = a.st_state[st_idx + 1];
+      sm.prev = v.x;
+      sm.cur = v.y;
+      sm.e = 0;
+    }
   }
   // four recursion steps s..s+3 of the current sub-chunk (s multiple of 4) and their stores.
   // Values that are not representable yet (extended exponent e < 0) are stored as zeros by a predicated second
@@ -179,7 +198,7 @@ __device__ __forceinline__ void park_coef(double *cf, double2 c2, int lsub, int 
 
 
 struct Setup {
-  int g, mi, m, l0, pb, nrows, nchunk;
+  int g, mi, m, l0, pb, nrows, nchunk, chk0;  // chk0: first chunk in which any chain of the CTA is representable
   i64 row0, cbase;
   i64 nrp_b, rp_base, poff;  // ring pairs of this CTA's block, its first ring pair, its offset in phase
 };
@@ -217,9 +236,112 @@ __device__ __forceinline__ bool setup_cta(const LegArgs &a, Setup &s, Rec<SPIN> 
     shh = a.sh[rp];
     rec.alive = !ring_is_dead(a.lmax, s.m, SPIN, rec.x, sth);
   }
+  rec.ssp = rec.ssm = 0;
+  rec.st_idx = 0;
+  s.chk0 = 0;
+  if (a.st_sub != nullptr) {
+    // the dead zone was walked when the table was built: every chain starts where it first is representable
+    __shared__ int s_first;
+    if (threadIdx.x == 0) s_first = 0x7fffffff;
+    __syncthreads();
+    const int nsub = 2 * s.nchunk;
+    int first = 0x7fffffff;
+    if (rec.alive) {
+      constexpr int NJ = SPIN == 0 ? 1 : 2;
+      rec.st_idx = ((i64)s.m * a.st_nrp + (s.rp_base + s.row0 + r)) * NJ;
+      rec.ssp = a.st_sub[rec.st_idx];
+      rec.ssm = SPIN == 0 ? 0x7fffffff : a.st_sub[rec.st_idx + 1];
+      first = min(rec.ssp, rec.ssm);
+      rec.alive = first < nsub;
+    }
+    first = __reduce_min_sync(0xffffffffu, first);
+    if (lane == 0 && first < nsub) atomicMin(&s_first, first);
+    __syncthreads();
+    if (s_first >= nsub) return false;  // nothing of this CTA ever becomes representable
+    s.chk0 = s_first >> 1;
+    return true;
+  }
   if (__syncthreads_or(rec.alive ? 1 : 0) == 0) return false;  // no ring of this CTA contributes
   if (rec.alive) lam_start<SPIN>(s.m, a.cmtab, sth, chh, shh, rec.sp, rec.sm);
   return true;
+}
+
+// start-state table (hcu_start): one thread per (m, ring pair) walks the dead zone ONCE with exactly the arithmetic of
+// Rec::step4 / end_sub (and of Chain in k_legendre2.cu), so that a chain started from the table continues bit for bit
+// like one that walked there itself.  sub[.] = first sub-chunk (16 l from l0) at whose START the chain's extended
+// exponent is 0; state[.] = (prev, cur) there.
+template <int SPIN>
+__global__ void start_table_kernel(int lmax, int nrp, const double *cth, const double *sth, const double *ch, const double *sh,
+                                   const double *coef, const double *cmtab, int *sub, double2 *state) {
+  constexpr int NJ = SPIN == 0 ? 1 : 2;
+  const int m = blockIdx.y;
+  const int rp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rp >= nrp) return;
+  const i64 o = ((i64)m * nrp + rp) * NJ;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    sub[o + j] = 0x7fffffff;
+    state[o + j] = make_double2(0., 0.);
+  }
+  const int l0 = (SPIN == 0) ? m : (m > 2 ? m : 2);
+  if (l0 > lmax) return;
+  const double x = cth[rp];
+  if (ring_is_dead(lmax, m, SPIN, x, sth[rp])) return;
+  LamState sp, sm;
+  sp.prev = sp.cur = 0; sp.e = 0;
+  sm.prev = sm.cur = 0; sm.e = 0;
+  lam_start<SPIN>(m, cmtab, sth[rp], ch[rp], sh[rp], sp, sm);
+  const i64 cbase = alm_index(lmax, 0, m);
+  const int nsub = 2 * ((lmax - l0 + LC) / LC);
+  bool donep = false, donem = (SPIN == 0);
+  for (int s = 0; s < nsub; ++s) {
+    if (!donep && sp.e == 0) {
+      sub[o] = s;
+      state[o] = make_double2(sp.prev, sp.cur);
+      donep = true;
+    }
+    if (SPIN != 0 && !donem && sm.e == 0) {
+      sub[o + 1] = s;
+      state[o + 1] = make_double2(sm.prev, sm.cur);
+      donem = true;
+    }
+    if (donep && donem) break;
+    for (int u = 0; u < SL; ++u) {
+      const int l = l0 + s * SL + u;
+      double cx = 0.0, cy = 0.0;  // the kernels' coefficient tiles are zero filled from lmax on
+      if (l < lmax) {
+        if (SPIN == 0) {
+          cx = coef[cbase + l];
+        } else {
+          const double2 c2 = reinterpret_cast<const double2 *>(coef)[cbase + l];
+          cx = c2.x;
+          cy = c2.y;
+        }
+      }
+      if (SPIN == 0) {
+        const double nw = fma(cx * x, sp.cur, -sp.prev);
+        sp.prev = sp.cur;
+        sp.cur = nw;
+      } else {
+        const double ap = fma(cx, x, cy), am = fma(cx, x, -cy);
+        const double np = fma(ap, sp.cur, -sp.prev);
+        const double nm = fma(am, sm.cur, -sm.prev);
+        sp.prev = sp.cur; sp.cur = np;
+        sm.prev = sm.cur; sm.cur = nm;
+      }
+    }
+    if (sp.e < 0 && max(__double2hiint(sp.cur) & 0x7ff00000, __double2hiint(sp.prev) & 0x7ff00000) >= 0x4c700000) {
+      sp.cur *= TWO_M400;
+      sp.prev *= TWO_M400;
+      sp.e += SCALE_STEP;
+    }
+    if (SPIN != 0 && sm.e < 0 &&
+        max(__double2hiint(sm.cur) & 0x7ff00000, __double2hiint(sm.prev) & 0x7ff00000) >= 0x4c700000) {
+      sm.cur *= TWO_M400;
+      sm.prev *= TWO_M400;
+      sm.e += SCALE_STEP;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -307,13 +429,15 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
   const int a_off0 = lam_off(fa, fb), a_off1 = lam_off(4 + fa, fb) - 32;
   const int nsub = 2 * st.nchunk;
   int n_rec = 0, n_acc = 0;
-  // ---- prologue: sub-chunk 0 ----
+  // ---- prologue: the first sub-chunk of chunk chk0 (chunk 0 without a start-state table) ----
+  const int chk0 = st.chk0, s0 = 2 * st.chk0;
   bool live_cur = false, live_nxt = false;
-  park_coef(coefs, fetch_coef<SPIN>(a, cbase, st.l0, lane), st.l0, lmax, lane);
-  stage_coef_async<SPIN>(coefs + SL * 2, a, cbase, st.l0 + SL, lane);  // coefficients of sub-chunk 1
+  park_coef(coefs, fetch_coef<SPIN>(a, cbase, st.l0 + s0 * SL, lane), st.l0 + s0 * SL, lmax, lane);
+  stage_coef_async<SPIN>(coefs + SL * 2, a, cbase, st.l0 + (s0 + 1) * SL, lane);  // coefficients of the next sub-chunk
   __syncwarp();
   if (warp_alive) {
-    live_cur = rec.sub_live();
+    rec.maybe_start(a, s0);
+    live_cur = rec.sub_live(s0);
     rec.begin_sub();
 #pragma unroll
     for (int s = 0; s < SL; s += 4) rec.step4(tiles, coefs, ring, pb, s);
@@ -359,7 +483,8 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
     }
   };
 
-  for (int chk = 0; chk < st.nchunk; ++chk) {
+  for (int chk = chk0; chk < st.nchunk; ++chk) {
+    const int rc = chk - chk0;  // flush buffers and barrier phases count from the first chunk that is processed
     const int lstart = st.l0 + chk * LC;
     // scale of this thread's flush outputs, fetched a chunk's worth of work ahead
     const int f_l = lstart + 2 * f_idx + (f_p ^ pb);
@@ -386,7 +511,8 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
       __syncwarp();  // coefficients of sub-chunk sidx + 1 have landed; everybody is done with those of sidx
       if (prod) stage_coef_async<SPIN>(coefs + (sidx & 1) * (SL * 2), a, cbase, st.l0 + (sidx + 2) * SL, lane);  // tile `sidx` and the coefficients of sub-chunk sidx + 1 are in place
       if (prod) {
-        live_nxt = rec.sub_live();
+        rec.maybe_start(a, sidx + 1);
+        live_nxt = rec.sub_live(sidx + 1);
         rec.begin_sub();
         if (sidx + 1 < nsub) n_rec += 1;
       }
@@ -399,7 +525,15 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
           // the four recursion groups go with k4 = 0, 2, 4, 6, so that the next tile is complete one k4 step
           // before the hand-over and the tail of the DFMA chain hides behind the last DMMAs
 #ifndef HCU_EXP_NOREC
+#ifdef HCU_REC_BURST
+          // experiment: the whole recursion of the next sub-chunk as one burst ahead of the DMMAs
+          if (k4 == 0) {
+#pragma unroll
+            for (int s = 0; s < SL; s += 4) rec.step4(tnxt, ccur, ring, pb, s);
+          }
+#else
           if (!(k4 & 1)) rec.step4(tnxt, ccur, ring, pb, (k4 >> 1) * 4);
+#endif
 #endif
           const double *ta = tcur + ((k4 & 1) ? a_off1 : a_off0) + 32 * k4;
           double af[NJ][2];
@@ -441,12 +575,12 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
     }
 #endif
     // ---- first the deferred reduction of the previous chunk, then park this chunk's partial tile ----
-    if (chk > 0) reduce_chunk(chk - 1, f_l_prev, f_sc_prev);
+    if (rc > 0) reduce_chunk(rc - 1, f_l_prev, f_sc_prev);
     f_l_prev = f_l;
     f_sc_prev = f_sc * f_fl;
-    if (lane == 0) flags[(chk & 1) * NW + warp] = chunk_live ? 1 : 0;
+    if (lane == 0) flags[(rc & 1) * NW + warp] = chunk_live ? 1 : 0;
     if (chunk_live) {
-      double *o = flush + (chk & 1) * K::FLUSH + warp * (K::C * FLS);
+      double *o = flush + (rc & 1) * K::FLUSH + warp * (K::C * FLS);
 #pragma unroll
       for (int p = 0; p < 2; ++p)
 #pragma unroll
@@ -459,12 +593,12 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
           }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(mbar + (chk & 1));
+    if (lane == 0) mbar_arrive(mbar + (rc & 1));
   }
 #ifdef HCU_EXP_NOFLUSH
   if (f_sc_prev == 1.2345e-300) atomicAdd(a.alm.p[0], f_sc_prev);
 #else
-  reduce_chunk(st.nchunk - 1, f_l_prev, f_sc_prev);
+  reduce_chunk(st.nchunk - 1 - chk0, f_l_prev, f_sc_prev);
 #endif
   if (lane == 0 && a.work && n_rec > 0) {
     atomicAdd(a.work, n_rec * 32.0 * SL);
@@ -555,21 +689,23 @@ __global__ void __launch_bounds__(NT, 1) legendre_synthesis_kernel(LegArgs a) {
 
   const int ring = lane;
   bool live_cur = false, live_nxt = false;
-  // ---- prologue: sub-chunk 0 and the a_lm of chunk 0 ----
-  fetch_alm(st.l0);
-  park_coef(coefs, fetch_coef<SPIN>(a, cbase, st.l0, lane), st.l0, lmax, lane);
-  stage_coef_async<SPIN>(coefs + SL * 2, a, cbase, st.l0 + SL, lane);  // coefficients of sub-chunk 1
+  // ---- prologue: the first sub-chunk and the a_lm of chunk chk0 (chunk 0 without a start-state table) ----
+  const int chk0 = st.chk0, s0 = 2 * st.chk0;
+  fetch_alm(st.l0 + chk0 * LC);
+  park_coef(coefs, fetch_coef<SPIN>(a, cbase, st.l0 + s0 * SL, lane), st.l0 + s0 * SL, lmax, lane);
+  stage_coef_async<SPIN>(coefs + SL * 2, a, cbase, st.l0 + (s0 + 1) * SL, lane);  // coefficients of the next sub-chunk
   __syncwarp();
   if (warp_alive) {
-    live_cur = rec.sub_live();
+    rec.maybe_start(a, s0);
+    live_cur = rec.sub_live(s0);
     rec.begin_sub();
 #pragma unroll
     for (int s = 0; s < SL; s += 4) rec.step4(tiles, coefs, ring, pb, s);
     rec.end_sub();
   }
-  park_alm(st.l0);
+  park_alm(st.l0 + chk0 * LC);
 
-  for (int chk = 0; chk < st.nchunk; ++chk) {
+  for (int chk = chk0; chk < st.nchunk; ++chk) {
     if (chk + 1 < st.nchunk) fetch_alm(st.l0 + (chk + 1) * LC);
 #pragma unroll
     for (int sb = 0; sb < 2; ++sb) {
@@ -582,7 +718,8 @@ __global__ void __launch_bounds__(NT, 1) legendre_synthesis_kernel(LegArgs a) {
       __syncwarp();  // coefficients of sub-chunk sidx + 1 have landed; everybody is done with those of sidx
       if (prod) stage_coef_async<SPIN>(coefs + (sidx & 1) * (SL * 2), a, cbase, st.l0 + (sidx + 2) * SL, lane);  // tile `sidx`, btile and the coefficients of sub-chunk sidx + 1 are in place
       if (prod) {
-        live_nxt = rec.sub_live();
+        rec.maybe_start(a, sidx + 1);
+        live_nxt = rec.sub_live(sidx + 1);
         rec.begin_sub();
       }
       if (live_cur) {
@@ -758,6 +895,9 @@ void fill_args(LegArgs &a, hcu_geom *g, hcu_coef *c, int lmax, int ncomp,
   a.fl = nullptr;
   a.phase_out = nullptr;
   a.work = nullptr;
+  a.st_sub = nullptr;
+  a.st_state = nullptr;
+  a.st_nrp = g->nrp;
 }
 
 }  // namespace
@@ -831,6 +971,27 @@ int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c) {
   return HCU_OK;
 }
 
+int hcu_build_start(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, hcu_start *t) {
+  const size_t n = (size_t)(c->lmax + 1) * g->nrp * (c->spin == 0 ? 1 : 2);
+  if (cudaMalloc(&t->sub, sizeof(int) * n) != cudaSuccess) {
+    t->sub = nullptr;
+    return HCU_ERR_NOMEM;
+  }
+  if (cudaMalloc(&t->state, sizeof(double2) * n) != cudaSuccess) {
+    cudaFree(t->sub);
+    t->sub = nullptr;
+    t->state = nullptr;
+    return HCU_ERR_NOMEM;
+  }
+  dim3 grid((g->nrp + 127) / 128, c->lmax + 1);
+  if (c->spin == 0)
+    start_table_kernel<0><<<grid, 128, 0, ctx->stream>>>(c->lmax, g->nrp, g->cth, g->sth, g->ch, g->sh, c->tab, c->cm, t->sub, t->state);
+  else
+    start_table_kernel<2><<<grid, 128, 0, ctx->stream>>>(c->lmax, g->nrp, g->cth, g->sth, g->ch, g->sh, c->tab, c->cm, t->sub, t->state);
+  HCU_LAUNCH_CHECK(ctx);
+  return HCU_OK;
+}
+
 // alm[c][l, m] += sum over the ring pairs of all blocks of lambda_lm(theta) x phase, for m in mlist
 int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
                           int spin, int ncomp, const double *phase,
@@ -844,7 +1005,14 @@ int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
   a.fl = fl_dev;
   a.alm = alm;
   a.work = ctx->work_counters;
-  if (legendre_gen(spin, ncomp, false) == 2) return hcu_legendre2_analysis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
+  const bool gen2 = legendre_gen(spin, ncomp, false) == 2;
+  hcu_start *tab = nullptr;
+  if (!gen2) HCU_CHECK(hcu_get_start(ctx, g, c, &tab));  // (the second-generation kernels walk the dead zone themselves)
+  if (tab) {
+    a.st_sub = tab->sub;
+    a.st_state = tab->state;
+  }
+  if (gen2) return hcu_legendre2_analysis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
   // 8 output columns per n-block: 4 spin-0 maps, or 2 spin-2 fields (4 Q/U rows)
   const int ncolblk = (ncomp + 3) / 4;
   if (spin == 0) {
@@ -869,6 +1037,12 @@ int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
   a.alm = alm;
   a.phase_out = phase;
   if (legendre_gen(spin, ncomp, true) == 2) return hcu_legendre2_synthesis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
+  hcu_start *tab = nullptr;
+  HCU_CHECK(hcu_get_start(ctx, g, c, &tab));
+  if (tab) {
+    a.st_sub = tab->sub;
+    a.st_state = tab->state;
+  }
   if (spin == 0) {
     switch ((ncomp + 3) / 4) {
       case 1: return launch_synthesis<0, 1>(ctx, a);

@@ -195,6 +195,11 @@ struct LegArgs {
   const double *scale;      // s_l of the scaled recursion, lambda_l = s_l q_l
   const double *cmtab;
   const double *fl;         // nullptr or [lmax+1]
+  // optional start-state table (hcu_get_start): where every recursion chain first becomes representable and its
+  // (prev, cur) there, indexed [(m * st_nrp + ring pair) * NJ + j]; nullptr: every chain starts at l0 (lam_start)
+  const int *st_sub;
+  const double2 *st_state;
+  int st_nrp;
   hcu_ptrs alm;             // one complex128 row per component
   double *phase_out;        // synthesis output, same layout as `phase` with (reN, imN, reS, imS)
   double *work;             // [2] counters

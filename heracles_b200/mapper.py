@@ -344,7 +344,8 @@ class CudaHealpixMapper:
         :meth:`map_page` accumulator: the values the reference's running means converge to
         (``heracles/fields.py:269-271, 430-433``); raises like ``CatalogPage.get`` if a NaN was seen.
         """
-        s = np.array(np.asarray(stats), dtype=np.float64)
+        # wait for the page kernels that are still updating the sums (map_page(sync=False) returns at once)
+        s = np.array(stats._host() if isinstance(stats, DeviceArray) else np.asarray(stats), dtype=np.float64)
         if s[7]:
             raise ValueError("invalid values in catalogue page columns")
         pos = (int(s[0]), s[1] / s[0], s[2] / s[0]) if s[0] else (0, 0.0, 0.0)

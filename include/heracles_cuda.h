@@ -230,6 +230,11 @@ int hcu_alm2cl_mslice(hcu_ctx *ctx, int na, const void *a, int64_t stride_a,
                       int lmax_out, int m_step, int m_offset, double *cl);
 
 /* ---- introspection --------------------------------------------------------- */
+/* The Legendre kernels skip the "dead zone" l0 <= l < l_start(m, ring) -- where lambda_lm is below 2^-200 and contributes
+ * nothing -- by starting every recursion from a table of start states built once per (nside, lmax, spin) with the same
+ * arithmetic (20 bytes per (m, ring pair, chain); not built when it would take more than a quarter of the free memory).
+ * Results are bit-identical with and without it; hcu_set_start_table(ctx, 0) disables it (A/B timing, tests). */
+int hcu_set_start_table(hcu_ctx *ctx, int enabled);
 /* stage timing is off by default (it costs a host wait per Legendre batch); hcu_set_timing(ctx, 1) enables it */
 int hcu_set_timing(hcu_ctx *ctx, int enabled);
 /* device milliseconds of the stages of the last hcu_map2alm / hcu_alm2map call

@@ -27,7 +27,8 @@ for arg in sys.argv[1:]:
         u = dict(zip(hdr, units))
         b = sum(float(d[k]) * UNIT[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         tot.append(b)
-    out[key] = sum(tot) / len(tot)
+    avg = sum(tot) / len(tot)
+    out[key] = None if avg != avg else avg  # NaN: a replay pass of the capture failed
     out.setdefault("_source", {})[key] = f"{os.path.basename(rep)} ({len(tot)} launch(es) of {kre or 'all kernels'})"
 json.dump(out, open(out_path, "w"), indent=1)
 print(json.dumps(out, indent=1))
