@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_shard_plan(nside, lmax, world):
     from heracles_b200.dist import ShardPlan
 
-    plan = ShardPlan(nside, lmax, world, fft_cost=None)
+    plan = ShardPlan(nside, lmax, world, fft_cost=None, align=1)
     assert plan.rp_bounds[0] == 0 and plan.rp_bounds[-1] == 2 * nside
     assert all(b > a for a, b in zip(plan.rp_bounds, plan.rp_bounds[1:]))
     # pixel ranges of the blocks tile the map exactly once
@@ -32,6 +32,10 @@ def test_shard_plan(nside, lmax, world):
     assert wr[0][0] == 0 and wr[-1][1] == wplan.npix and all(a[1] == b[0] for a, b in zip(wr, wr[1:]))
     if world > 1 and nside >= 64:
         assert sum(b - a for a, b in wplan.pixel_ranges(0)) < sizes[0]
+    # ... with boundaries on multiples of the 256 ring pairs one Legendre CTA works on, so that no CTA runs partly empty
+    if 2 * nside >= 2 * 256 * world:
+        assert all(b % 256 == 0 for b in wplan.rp_bounds)
+        assert sum(-(-(b - a) // 256) for a, b in zip(wplan.rp_bounds, wplan.rp_bounds[1:])) == 2 * nside // 256
     # every m has exactly one owner and the row order is the concatenation of the owners' lists
     assert sorted(plan.m_all.tolist()) == list(range(lmax + 1))
     assert all(plan.owner_of_m(int(m)) == g for g in range(world) for m in plan.mlists[g])
