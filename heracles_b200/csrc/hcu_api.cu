@@ -91,6 +91,7 @@ extern "C" int hcu_trim(hcu_ctx *ctx) {
   free_buffer(&ctx->ws_phase);
   free_buffer(&ctx->ws_belt);
   free_buffer(&ctx->ws_cap);
+  free_buffer(&ctx->ws_scr);
   free_buffer(&ctx->ws_map);
   free_buffer(&ctx->ws_alm);
   free_buffer(&ctx->ws_misc);
@@ -112,6 +113,7 @@ extern "C" int hcu_destroy(hcu_ctx *ctx) {
     cudaFree(kv.second.sh);
     if (kv.second.bfilt) cudaFree(kv.second.bfilt);
     if (kv.second.bfilt_off) cudaFree(kv.second.bfilt_off);
+    hcu_ring2_free(&kv.second);
   }
   for (auto &kv : ctx->start) {
     if (kv.second.sub) cudaFree(kv.second.sub);

@@ -80,6 +80,12 @@ struct hcu_geom {
   double2 *bfilt = nullptr; // concatenated, bit-reversed FFT_M(chirp)/M
   i64 *bfilt_off = nullptr; // [nside] offsets (device)
   std::vector<i64> bfilt_off_h;
+  // second-generation ring FFT (k_ringfft2.cu): pass twiddles for 2^4 .. 2^13 points, per-ring chirp and radix-4
+  // twiddle tables of the cap rings 1 .. r2_imax, radix-4 twiddles of the belt
+  double2 *r2_tw = nullptr, *r2_chirp = nullptr, *r2_wtab = nullptr, *r2_wbelt = nullptr;
+  int r2_tw_off[14] = {0};
+  int r2_imax = 0;      // largest cap ring number handled by the second generation (0: none)
+  bool r2_belt = false; // belt handled by the second generation
 };
 
 // per-(lmax, spin) recursion coefficient table
@@ -120,7 +126,7 @@ struct hcu_ctx {
   int next_slot = 0;
   unsigned long long *bad_rows = nullptr; // device counter
   // workspaces
-  hcu_buffer ws_phase, ws_belt, ws_cap, ws_map, ws_alm, ws_misc, ws_state, ws_resid, ws_pw;
+  hcu_buffer ws_phase, ws_belt, ws_cap, ws_scr, ws_map, ws_alm, ws_misc, ws_state, ws_resid, ws_pw;
   // tables
   std::map<i64, hcu_geom> geom;
   std::map<std::pair<int, int>, hcu_coef> coef;
@@ -154,6 +160,12 @@ int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
 int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
                          const double *phase, const int32_t *mpos, i64 rp_lo, i64 rp_hi,
                          const hcu_ptrs &maps);
+// second generation (k_ringfft2.cu)
+int hcu_ring2_build(hcu_ctx *ctx, hcu_geom *g, int cap_max_m);
+void hcu_ring2_free(hcu_geom *g);
+int hcu_ring2_run(hcu_ctx *ctx, hcu_geom *g, bool inverse, bool belt, int lmax, int ncomp, const hcu_ptrs &maps,
+                  const double *ring_weights, i64 rp_lo, i64 nrp_local, i64 rp_a, i64 rp_b, const int32_t *mlist,
+                  int nm, const int32_t *mpos, double *phase);
 int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c);
 int hcu_legendre_batch(int spin);  // components one Legendre launch can take: 12 (spin 0), 8 (spin 2)
 // (both Legendre launchers look the start-state table up themselves)

@@ -18,6 +18,8 @@
 // HBM-bound: algorithmic bytes = 8 npix (map read) + 32 nrp (lmax+1) (phase write) per component.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "hcu_common.cuh"
 
 namespace {
@@ -584,7 +586,7 @@ int hcu_build_bluestein(hcu_ctx *ctx, hcu_geom *g) {
     g->bfilt_off_h[i] = total;
     total += bluestein_M(i);
   }
-  if (total == 0) return HCU_OK;
+  if (total == 0) return hcu_ring2_build(ctx, g, cap_max_m());
   HCU_CUDA(cudaMalloc(&g->bfilt, sizeof(double2) * total));
   HCU_CUDA(cudaMalloc(&g->bfilt_off, sizeof(i64) * (nside + 1)));
   HCU_CUDA(cudaMemcpyAsync(g->bfilt_off, g->bfilt_off_h.data(), sizeof(i64) * (nside + 1),
@@ -610,7 +612,7 @@ int hcu_build_bluestein(hcu_ctx *ctx, hcu_geom *g) {
     HCU_LAUNCH_CHECK(ctx);
     i = ihi + 1;
   }
-  return HCU_OK;
+  return hcu_ring2_build(ctx, g, cap_max_m());
 }
 
 // cuFFT plan-many over `batch` consecutive belt rings (cached per nside, batch and direction)
@@ -652,6 +654,110 @@ static int belt_runs(i64 nside, i64 belt_lo, i64 belt_hi, i64 run0[2], i64 cnt[2
   return 2;
 }
 
+// comp stride of the first-generation cap workspace that covers north ring numbers <= imax
+static i64 cap_stride(i64 imax) { return 2 * imax * (imax + 1); }
+
+// first-generation cap transforms of ring pairs [lo, hi): sub-FFTs into Y, then the post kernel
+static int old_caps_forward(hcu_ctx *ctx, hcu_geom *g, int ncomp, const hcu_ptrs &maps, const double *ring_weights,
+                            i64 rp_lo, i64 nrp_local, i64 lo, i64 hi, const int32_t *mlist, int nm, double *phase,
+                            i64 ystride) {
+  if (lo >= hi) return HCU_OK;
+  const i64 nside = g->nside;
+  const int mthreads = 128;
+  const unsigned mblocks = (unsigned)((nm + mthreads - 1) / mthreads);
+  double2 *Y = (double2 *)ctx->ws_cap.ptr;
+  int i = (int)lo + 1;
+  const int iend = (int)hi;  // inclusive ring number
+  while (i <= iend) {
+    int M = bluestein_M(i);
+    int ihi = i;
+    while (ihi + 1 <= iend && bluestein_M(ihi + 1) == M) ++ihi;
+    dim3 grid(ihi - i + 1, ncomp);
+    if (M > cap_max_m()) {
+      const int Mh = M / 2;
+      size_t smem = (size_t)Mh * 24;
+      HCU_CUDA(cudaFuncSetAttribute(cap_fft_fwd_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cap_fft_fwd_big_kernel<<<grid, cap_threads(Mh), smem, ctx->stream>>>(i, Mh, nside, maps, g->bfilt,
+                                                                           g->bfilt_off, Y, ystride);
+    } else {
+      size_t smem = (size_t)M * 24;
+      HCU_CUDA(cudaFuncSetAttribute(cap_fft_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cap_fft_fwd_kernel<<<grid, cap_threads(M), smem, ctx->stream>>>(i, M, nside, maps, g->bfilt, g->bfilt_off, Y,
+                                                                      ystride);
+    }
+    HCU_LAUNCH_CHECK(ctx);
+    i = ihi + 1;
+  }
+  dim3 grid(mblocks, (unsigned)(hi - lo), (unsigned)ncomp);
+  cap_post_kernel<<<grid, mthreads, 0, ctx->stream>>>(nside, nm, mlist, ncomp, Y, ystride, ring_weights, rp_lo,
+                                                      nrp_local, lo, phase);
+  HCU_LAUNCH_CHECK(ctx);
+  return HCU_OK;
+}
+
+static int old_caps_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp, const double *phase, const int32_t *mpos,
+                            i64 rp_lo, i64 nrp_local, i64 lo, i64 hi, const hcu_ptrs &maps, i64 zstride) {
+  if (lo >= hi) return HCU_OK;
+  const i64 nside = g->nside;
+  double2 *Z = (double2 *)ctx->ws_cap.ptr;
+  dim3 pgrid((unsigned)((4 * hi + 127) / 128), (unsigned)(hi - lo), (unsigned)ncomp);
+  cap_pre_inv_kernel<<<pgrid, 128, 0, ctx->stream>>>(nside, lmax, mpos, ncomp, phase, rp_lo, nrp_local, lo, Z,
+                                                     zstride);
+  HCU_LAUNCH_CHECK(ctx);
+  int i = (int)lo + 1;
+  const int iend = (int)hi;
+  while (i <= iend) {
+    int M = bluestein_M(i);
+    int ihi = i;
+    while (ihi + 1 <= iend && bluestein_M(ihi + 1) == M) ++ihi;
+    dim3 grid(ihi - i + 1, ncomp);
+    if (M > cap_max_m()) {
+      const int Mh = M / 2;
+      size_t smem = (size_t)Mh * 24;
+      HCU_CUDA(cudaFuncSetAttribute(cap_fft_inv_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cap_fft_inv_big_kernel<<<grid, cap_threads(Mh), smem, ctx->stream>>>(i, Mh, nside, Z, zstride, g->bfilt,
+                                                                           g->bfilt_off, maps);
+    } else {
+      size_t smem = (size_t)M * 24;
+      HCU_CUDA(cudaFuncSetAttribute(cap_fft_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cap_fft_inv_kernel<<<grid, cap_threads(M), smem, ctx->stream>>>(i, M, nside, Z, zstride, g->bfilt, g->bfilt_off,
+                                                                      maps);
+    }
+    HCU_LAUNCH_CHECK(ctx);
+    i = ihi + 1;
+  }
+  return HCU_OK;
+}
+
+// split of the cap ring pairs [cap_lo, cap_hi) between the generations: the second generation takes north ring
+// numbers 5 .. r2_imax (ring pairs [4, r2_imax)), the first generation what lies below and above
+struct cap_split {
+  i64 a_lo, a_hi;  // first generation, tiny rings
+  i64 n_lo, n_hi;  // second generation
+  i64 b_lo, b_hi;  // first generation, rings beyond one CTA's shared memory
+  i64 ystride;     // comp stride of the first generation's workspace (0: none needed)
+};
+static cap_split split_caps(const hcu_geom *g, i64 cap_lo, i64 cap_hi) {
+  cap_split s;
+  const i64 imax = g->r2_imax;
+  if (imax < 5) {
+    s.a_lo = cap_lo, s.a_hi = cap_hi;
+    s.n_lo = s.n_hi = s.b_lo = s.b_hi = cap_hi;
+  } else {
+    s.a_lo = cap_lo, s.a_hi = std::min<i64>(cap_hi, 4);
+    s.n_lo = std::max<i64>(cap_lo, 4), s.n_hi = std::min<i64>(cap_hi, imax);
+    s.b_lo = std::max<i64>(cap_lo, imax), s.b_hi = cap_hi;
+  }
+  if (s.a_lo > s.a_hi) s.a_hi = s.a_lo;
+  if (s.n_lo > s.n_hi) s.n_hi = s.n_lo;
+  if (s.b_lo > s.b_hi) s.b_hi = s.b_lo;
+  i64 top = 0;
+  if (s.a_lo < s.a_hi) top = s.a_hi;
+  if (s.b_lo < s.b_hi) top = s.b_hi;
+  s.ystride = top ? cap_stride(top) : 0;
+  return s;
+}
+
 // forward ring FFT stage for ring pairs [rp_lo, rp_hi) of ncomp maps; phase rows follow mlist (nm rows)
 int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
                          const hcu_ptrs &maps, const double *ring_weights,
@@ -663,47 +769,27 @@ int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
   const int nk = n4 / 2 + 1;
   const int mthreads = 128;
   const unsigned mblocks = (unsigned)((nm + mthreads - 1) / mthreads);
-  (void)lmax;
   if (nm <= 0 || nrp_local <= 0) return HCU_OK;
 
   // ---- polar caps: ring pairs rp < nside - 1 ---------------------------------
   i64 cap_lo = rp_lo, cap_hi = rp_hi < nside - 1 ? rp_hi : nside - 1;
   if (cap_lo < cap_hi) {
-    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_cap, sizeof(double2) * (size_t)ncap * ncomp));
-    double2 *Y = (double2 *)ctx->ws_cap.ptr;
-    int i = (int)cap_lo + 1;
-    const int iend = (int)cap_hi;  // inclusive ring number
-    while (i <= iend) {
-      int M = bluestein_M(i);
-      int ihi = i;
-      while (ihi + 1 <= iend && bluestein_M(ihi + 1) == M) ++ihi;
-      dim3 grid(ihi - i + 1, ncomp);
-      if (M > cap_max_m()) {
-        const int Mh = M / 2;
-        size_t smem = (size_t)Mh * 24;
-        HCU_CUDA(cudaFuncSetAttribute(cap_fft_fwd_big_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cap_fft_fwd_big_kernel<<<grid, cap_threads(Mh), smem, ctx->stream>>>(
-            i, Mh, nside, maps, g->bfilt, g->bfilt_off, Y, ncap);
-      } else {
-        size_t smem = (size_t)M * 24;
-        HCU_CUDA(cudaFuncSetAttribute(cap_fft_fwd_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cap_fft_fwd_kernel<<<grid, cap_threads(M), smem, ctx->stream>>>(
-            i, M, nside, maps, g->bfilt, g->bfilt_off, Y, ncap);
-      }
-      HCU_LAUNCH_CHECK(ctx);
-      i = ihi + 1;
-    }
-    dim3 grid(mblocks, (unsigned)(cap_hi - cap_lo), (unsigned)ncomp);
-    cap_post_kernel<<<grid, mthreads, 0, ctx->stream>>>(nside, nm, mlist, ncomp, Y, ncap, ring_weights,
-                                                        rp_lo, nrp_local, cap_lo, phase);
-    HCU_LAUNCH_CHECK(ctx);
+    const cap_split cs = split_caps(g, cap_lo, cap_hi);
+    if (cs.ystride) HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_cap, sizeof(double2) * (size_t)cs.ystride * ncomp));
+    HCU_CHECK(old_caps_forward(ctx, g, ncomp, maps, ring_weights, rp_lo, nrp_local, cs.b_lo, cs.b_hi, mlist, nm,
+                               phase, cs.ystride));
+    HCU_CHECK(hcu_ring2_run(ctx, g, false, false, lmax, ncomp, maps, ring_weights, rp_lo, nrp_local, cs.n_lo, cs.n_hi,
+                            mlist, nm, nullptr, phase));
+    HCU_CHECK(old_caps_forward(ctx, g, ncomp, maps, ring_weights, rp_lo, nrp_local, cs.a_lo, cs.a_hi, mlist, nm,
+                               phase, cs.ystride));
   }
 
   // ---- equatorial belt: ring pairs rp >= nside - 1 -------------------------------
   i64 belt_lo = rp_lo > nside - 1 ? rp_lo : nside - 1, belt_hi = rp_hi;
-  if (belt_lo < belt_hi) {
+  if (belt_lo < belt_hi && g->r2_belt) {
+    HCU_CHECK(hcu_ring2_run(ctx, g, false, true, lmax, ncomp, maps, ring_weights, rp_lo, nrp_local, belt_lo, belt_hi,
+                            mlist, nm, nullptr, phase));
+  } else if (belt_lo < belt_hi) {
     HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_belt, sizeof(double2) * (size_t)nk * (2 * nside + 1)));
     double2 *X = (double2 *)ctx->ws_belt.ptr;
     i64 run0[2], cnt[2];
@@ -739,40 +825,19 @@ int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
   // caps
   i64 cap_lo = rp_lo, cap_hi = rp_hi < nside - 1 ? rp_hi : nside - 1;
   if (cap_lo < cap_hi) {
-    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_cap, sizeof(double2) * (size_t)ncap * ncomp));
-    double2 *Z = (double2 *)ctx->ws_cap.ptr;
-    dim3 pgrid((unsigned)((4 * cap_hi + 127) / 128), (unsigned)(cap_hi - cap_lo), (unsigned)ncomp);
-    cap_pre_inv_kernel<<<pgrid, 128, 0, ctx->stream>>>(nside, lmax, mpos, ncomp, phase, rp_lo, nrp_local,
-                                                       cap_lo, Z, ncap);
-    HCU_LAUNCH_CHECK(ctx);
-    int i = (int)cap_lo + 1;
-    const int iend = (int)cap_hi;
-    while (i <= iend) {
-      int M = bluestein_M(i);
-      int ihi = i;
-      while (ihi + 1 <= iend && bluestein_M(ihi + 1) == M) ++ihi;
-      dim3 grid(ihi - i + 1, ncomp);
-      if (M > cap_max_m()) {
-        const int Mh = M / 2;
-        size_t smem = (size_t)Mh * 24;
-        HCU_CUDA(cudaFuncSetAttribute(cap_fft_inv_big_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cap_fft_inv_big_kernel<<<grid, cap_threads(Mh), smem, ctx->stream>>>(
-            i, Mh, nside, Z, ncap, g->bfilt, g->bfilt_off, maps);
-      } else {
-        size_t smem = (size_t)M * 24;
-        HCU_CUDA(cudaFuncSetAttribute(cap_fft_inv_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cap_fft_inv_kernel<<<grid, cap_threads(M), smem, ctx->stream>>>(
-            i, M, nside, Z, ncap, g->bfilt, g->bfilt_off, maps);
-      }
-      HCU_LAUNCH_CHECK(ctx);
-      i = ihi + 1;
-    }
+    const cap_split cs = split_caps(g, cap_lo, cap_hi);
+    if (cs.ystride) HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_cap, sizeof(double2) * (size_t)cs.ystride * ncomp));
+    HCU_CHECK(old_caps_inverse(ctx, g, lmax, ncomp, phase, mpos, rp_lo, nrp_local, cs.b_lo, cs.b_hi, maps, cs.ystride));
+    HCU_CHECK(hcu_ring2_run(ctx, g, true, false, lmax, ncomp, maps, nullptr, rp_lo, nrp_local, cs.n_lo, cs.n_hi,
+                            nullptr, 0, mpos, const_cast<double *>(phase)));
+    HCU_CHECK(old_caps_inverse(ctx, g, lmax, ncomp, phase, mpos, rp_lo, nrp_local, cs.a_lo, cs.a_hi, maps, cs.ystride));
   }
   // belt
   i64 belt_lo = rp_lo > nside - 1 ? rp_lo : nside - 1, belt_hi = rp_hi;
-  if (belt_lo < belt_hi) {
+  if (belt_lo < belt_hi && g->r2_belt) {
+    HCU_CHECK(hcu_ring2_run(ctx, g, true, true, lmax, ncomp, maps, nullptr, rp_lo, nrp_local, belt_lo, belt_hi, nullptr,
+                            0, mpos, const_cast<double *>(phase)));
+  } else if (belt_lo < belt_hi) {
     HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_belt, sizeof(double2) * (size_t)nk * (2 * nside + 1)));
     double2 *X = (double2 *)ctx->ws_belt.ptr;
     i64 run0[2], cnt[2];

@@ -435,6 +435,35 @@ print("ok")
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
 
 
+def test_first_generation_ring_fft():
+    """HCU_RINGFFT_GEN=1 keeps the first-generation ring-FFT kernels (cuFFT belt, one-sub-sequence cap kernels) for
+    every ring -- the path that still serves ring numbers < 5, nside < 16 and the rings beyond one CTA's shared
+    memory: same oracle check as the default (second-generation, k_ringfft2.cu) path gets everywhere else."""
+    import os
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    code = r"""
+import numpy as np, oracle, heracles_b200 as hb
+oracle.build()
+for nside, lmax in ((32, 64), (128, 300)):
+    rng = np.random.default_rng(4)
+    maps = rng.standard_normal((4, 12 * nside * nside))
+    for spin in (0, 2):
+        mapper = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=2)
+        a = np.asarray(mapper.transform(maps if spin == 0 else maps.reshape(2, 2, -1), spin=spin)).reshape(4, -1)
+        r = oracle.map2alm(nside, lmax, maps, spin=spin, niter=2)
+        err = np.linalg.norm(a - r) / np.linalg.norm(r)
+        assert err < 1e-10, (nside, spin, err)
+print("ok")
+"""
+    env = dict(os.environ, HCU_RINGFFT_GEN="1", PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_sparse_map_nside_8192(hb, oracle):
     """BASELINE.json config 5 resolution (nside 8192, lmax 16384): sparse-map closed form, spin 0"""
     nside, lmax = 8192, 16384
