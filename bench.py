@@ -185,7 +185,7 @@ class Pipeline:
         self.dist = None
         if world > 1:
             # ring-block / m-distributed transform over the ranks (heracles_b200/dist.py)
-            from heracles_b200.dist import DistributedTransform, ShardPlan, make_lanes
+            from heracles_b200.dist import DistributedTransform, ShardPlan, attach_peers, make_lanes
 
             self.plan = ShardPlan(nside, lmax, world)
             # HCU_BENCH_LANES=2: the FFT / all-to-all stages of one Legendre batch are queued under the Legendre kernels of
@@ -195,6 +195,8 @@ class Pipeline:
             self.lanes = make_lanes(self.ctx, nside, lmax, int(os.environ.get("HCU_BENCH_LANES", "1")))
             for lane in self.lanes:
                 lane.k.ctx.set_timing(True)
+            # exchange through NVLink peer memory (HCU_DIST_EXCHANGE=nccl: all_to_all_single)
+            attach_peers(self.lanes, lambda lane: lane.k.ctx, self.plan, rank, torch.device("cuda"))
             self.kernels = self.lanes[0].k
             self.dist = DistributedTransform(self.kernels, self.plan, rank, niter=niter, device=torch.device("cuda"), lanes=self.lanes)
             from heracles_b200.dist import _reduce_group
@@ -1021,6 +1023,9 @@ def main():
     }
     if pipe.dist is not None:
         line["dist_stage_ms_per_rank"] = dist_stage
+        line["dist_exchange"] = ("peer: ring-FFT / Legendre-synthesis kernels write the phase rows into the consuming rank's buffer over "
+                                 "NVLink peer memory (CUDA IPC), one 1-element all-reduce per stage as the barrier"
+                                 if pipe.lanes[0].peers is not None else "nccl: all_to_all_single")
         line["dist_parity"] = dist_parity
 
     # end to end through the plugin API, host pages

@@ -62,6 +62,24 @@ struct hcu_ptrs {
   double *p[HCU_MAX_BATCH];
 };
 
+// Destinations of the phase rows a ring-FFT launch writes (multi-GPU: rows are ordered by the rank that owns their m,
+// and every rank's rows go STRAIGHT into that rank's buffer over NVLink peer memory): rows [row_start[d],
+// row_start[d+1]) live at base[d] + (row - row_start[d]) * (nrp_local * ncomp * 4).  nd == 0: one local array.
+#define HCU_MAX_BLOCKS 16
+struct hcu_rowdest {
+  int nd = 0;
+  int row_start[HCU_MAX_BLOCKS + 1];
+  double *base[HCU_MAX_BLOCKS];
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ double *hcu_row_ptr(const hcu_rowdest &rd, double *phase, int row, i64 rstride) {
+  if (rd.nd == 0) return phase + (i64)row * rstride;
+  int d = 0;
+  while (d + 1 < rd.nd && row >= rd.row_start[d + 1]) ++d;
+  return rd.base[d] + (i64)(row - rd.row_start[d]) * rstride;
+}
+#endif
+
 // a growable device workspace
 struct hcu_buffer {
   void *ptr = nullptr;
@@ -156,7 +174,8 @@ int hcu_launch_map_values(hcu_ctx *ctx, i64 nside, int scheme, const double *lon
 int hcu_build_bluestein(hcu_ctx *ctx, hcu_geom *g);
 int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
                          const hcu_ptrs &maps, const double *ring_weights,
-                         i64 rp_lo, i64 rp_hi, const int32_t *mlist, int nm, double *phase);
+                         i64 rp_lo, i64 rp_hi, const int32_t *mlist, int nm, double *phase,
+                         const hcu_rowdest *dest = nullptr);
 int hcu_ring_fft_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
                          const double *phase, const int32_t *mpos, i64 rp_lo, i64 rp_hi,
                          const hcu_ptrs &maps);
@@ -165,7 +184,7 @@ int hcu_ring2_build(hcu_ctx *ctx, hcu_geom *g, int cap_max_m);
 void hcu_ring2_free(hcu_geom *g);
 int hcu_ring2_run(hcu_ctx *ctx, hcu_geom *g, bool inverse, bool belt, int lmax, int ncomp, const hcu_ptrs &maps,
                   const double *ring_weights, i64 rp_lo, i64 nrp_local, i64 rp_a, i64 rp_b, const int32_t *mlist,
-                  int nm, const int32_t *mpos, double *phase);
+                  int nm, const int32_t *mpos, double *phase, const hcu_rowdest *dest = nullptr);
 int hcu_build_coef(hcu_ctx *ctx, hcu_coef *c);
 int hcu_legendre_batch(int spin);  // components one Legendre launch can take: 12 (spin 0), 8 (spin 2)
 // (both Legendre launchers look the start-state table up themselves)
@@ -176,7 +195,7 @@ int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
 int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
                            int spin, int ncomp, const hcu_ptrs &alm,
                            const int32_t *mlist_dev, int nm, int nblk, const i64 *rp_bounds,
-                           double *phase);
+                           double *phase, double *const *block_out = nullptr);
 
 static inline int ilog2_host(i64 v) {
   int r = 0;

@@ -1,6 +1,8 @@
 // hcu_transform.cu -- orchestration of the spherical-harmonic transform stages
 // (ring FFT <-> Legendre), batching over maps, Jacobi iterations, staging of
 // host-resident inputs/outputs.  See include/heracles_cuda.h.
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -338,6 +340,34 @@ extern "C" int hcu_map2phase(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp,
   return hcu_ring_fft_forward(ctx, g, lmax, ncomp, src, ring_weights, rp_lo, rp_hi, mlist, nm, phase);
 }
 
+// The same ring FFTs with the rows of every destination rank written straight into that rank's buffer (peer memory)
+extern "C" int hcu_map2phase_peers(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp, const double *maps,
+                                   int64_t map_stride, const double *ring_weights, int64_t rp_lo, int64_t rp_hi,
+                                   const int32_t *mlist, int nm, int ndest, const int32_t *row_start,
+                                   double *const *dest_base) {
+  HCU_CHECK(check_stage_args(ctx, nside, lmax, 0, ncomp, rp_lo, rp_hi, mlist, nm));
+  HCU_ARG(maps && row_start && dest_base, "null pointer");
+  HCU_ARG(ndest >= 1 && ndest <= HCU_MAX_BLOCKS, "1 <= destinations <= 16");
+  HCU_ARG(row_start[0] == 0 && row_start[ndest] == nm, "row_start must cover the nm rows");
+  HCU_ARG(hcu_dev_accessible(maps), "device pointers required");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  hcu_geom *g;
+  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
+  hcu_ptrs src;
+  for (int c = 0; c < HCU_MAX_BATCH; ++c)
+    src.p[c] = c < ncomp ? const_cast<double *>(maps) + (i64)c * map_stride : nullptr;
+  hcu_rowdest dest;
+  dest.nd = ndest;
+  for (int d = 0; d < ndest; ++d) {
+    HCU_ARG(row_start[d] <= row_start[d + 1], "row_start must ascend");
+    HCU_ARG(dest_base[d] || row_start[d] == row_start[d + 1], "null destination");
+    dest.row_start[d] = row_start[d];
+    dest.base[d] = dest_base[d];
+  }
+  dest.row_start[ndest] = row_start[ndest];
+  return hcu_ring_fft_forward(ctx, g, lmax, ncomp, src, ring_weights, rp_lo, rp_hi, mlist, nm, nullptr, &dest);
+}
+
 extern "C" int hcu_phase2alm(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp,
                              const double *phase, const int32_t *mlist, int nm,
                              int64_t rp_lo, int64_t rp_hi, const double *fl, void *alm,
@@ -416,6 +446,54 @@ extern "C" int hcu_alm2phase_blocks(hcu_ctx *ctx, int64_t nside, int lmax, int s
     rows.p[c] = c < ncomp ? (double *)alm + 2 * (i64)c * alm_stride : nullptr;
   return hcu_legendre_synthesis(ctx, g, cf, lmax, spin, ncomp, rows, mlist, nm, nblocks,
                                 (const i64 *)rp_bounds, phase);
+}
+
+// hcu_alm2phase_blocks with block b written to block_out[b] (the buffer of the rank that owns those ring pairs)
+extern "C" int hcu_alm2phase_peers(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp, const void *alm,
+                                   int64_t alm_stride, const int32_t *mlist, int nm, int nblocks,
+                                   const int64_t *rp_bounds, double *const *block_out) {
+  HCU_ARG(rp_bounds && block_out && nblocks >= 1 && nblocks <= 16, "1 <= nblocks <= 16");
+  for (int b = 0; b < nblocks; ++b) {
+    HCU_ARG(rp_bounds[b] <= rp_bounds[b + 1], "rp_bounds must ascend");
+    HCU_ARG(block_out[b] || rp_bounds[b] == rp_bounds[b + 1], "null block destination");
+  }
+  HCU_CHECK(check_stage_args(ctx, nside, lmax, spin, ncomp, rp_bounds[0], rp_bounds[nblocks], mlist, nm));
+  HCU_ARG(alm && hcu_dev_accessible(alm), "device pointers required");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  hcu_geom *g;
+  hcu_coef *cf;
+  HCU_CHECK(hcu_get_geom(ctx, nside, &g));
+  HCU_CHECK(hcu_get_coef(ctx, lmax, spin, &cf));
+  hcu_ptrs rows;
+  for (int c = 0; c < HCU_MAX_BATCH; ++c)
+    rows.p[c] = c < ncomp ? (double *)alm + 2 * (i64)c * alm_stride : nullptr;
+  return hcu_legendre_synthesis(ctx, g, cf, lmax, spin, ncomp, rows, mlist, nm, nblocks, (const i64 *)rp_bounds,
+                                nullptr, block_out);
+}
+
+// ---- peer memory: export a cudaMalloc'ed buffer to the other ranks of the node, open theirs ----------------------
+extern "C" int hcu_ipc_export(hcu_ctx *ctx, const void *ptr, void *handle64) {
+  HCU_ARG(ctx && ptr && handle64, "null pointer");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  HCU_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(ptr)));
+  memcpy(handle64, &h, 64);
+  return HCU_OK;
+}
+extern "C" int hcu_ipc_open(hcu_ctx *ctx, const void *handle64, void **ptr) {
+  HCU_ARG(ctx && ptr && handle64, "null pointer");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  HCU_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return HCU_OK;
+}
+extern "C" int hcu_ipc_close(hcu_ctx *ctx, void *ptr) {
+  HCU_ARG(ctx && ptr, "null pointer");
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  HCU_CUDA(cudaIpcCloseMemHandle(ptr));
+  return HCU_OK;
 }
 
 extern "C" int hcu_phase2map(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp, const double *phase,

@@ -201,6 +201,7 @@ struct Setup {
   int g, mi, m, l0, pb, nrows, nchunk, chk0;  // chk0: first chunk in which any chain of the CTA is representable
   i64 row0, cbase;
   i64 nrp_b, rp_base, poff;  // ring pairs of this CTA's block, its first ring pair, its offset in phase
+  double *out;                // base of the block in the synthesis output
 };
 
 template <int SPIN>
@@ -213,6 +214,7 @@ __device__ __forceinline__ bool setup_cta(const LegArgs &a, Setup &s, Rec<SPIN> 
   s.nrp_b = a.blk_rp[b + 1] - a.blk_rp[b];
   s.rp_base = a.blk_rp[b];
   s.poff = (i64)a.nm * a.ncomp * 4 * (a.blk_rp[b] - a.blk_rp[0]);
+  s.out = a.use_blk_out ? a.blk_out[b] : a.phase_out + s.poff;
   s.m = a.mlist ? a.mlist[s.mi] : s.mi;
   s.l0 = (SPIN == 0) ? s.m : (s.m > 2 ? s.m : 2);
   s.row0 = (i64)(s.g - a.grp_start[b]) * R;
@@ -631,7 +633,7 @@ __global__ void __launch_bounds__(NT, 1) legendre_synthesis_kernel(LegArgs a) {
   Setup st;
   Rec<SPIN> rec;
   const bool active = setup_cta<SPIN>(a, st, rec, warp, lane);
-  double *dst = a.phase_out + st.poff + ((i64)st.mi * st.nrp_b + st.row0) * a.ncomp * 4;
+  double *dst = st.out + ((i64)st.mi * st.nrp_b + st.row0) * a.ncomp * 4;
   if (!active) {  // every output row must be defined
     for (int i = threadIdx.x; i < st.nrows * a.ncomp * 4; i += NT) dst[i] = 0.0;
     return;
@@ -879,6 +881,8 @@ void fill_args(LegArgs &a, hcu_geom *g, hcu_coef *c, int lmax, int ncomp,
   a.mlist = mlist_dev;
   a.phase = nullptr;
   a.nblk = nblk;
+  a.use_blk_out = 0;
+  a.phase_out = nullptr;
   a.grp_start[0] = 0;
   for (int b = 0; b < nblk; ++b) {
     a.blk_rp[b] = rp_bounds[b];
@@ -1029,13 +1033,17 @@ int hcu_legendre_analysis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
 int hcu_legendre_synthesis(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, int lmax,
                            int spin, int ncomp, const hcu_ptrs &alm,
                            const int32_t *mlist_dev, int nm, int nblk, const i64 *rp_bounds,
-                           double *phase) {
+                           double *phase, double *const *block_out) {
   HCU_ARG(ncomp >= 1 && ncomp <= hcu_legendre_batch(spin), "synthesis batch size");
   HCU_ARG(nblk >= 1 && nblk <= HCU_MAX_BLOCKS, "1 <= ring-pair blocks <= 16");
   LegArgs a;
   fill_args(a, g, c, lmax, ncomp, mlist_dev, nm, nblk, rp_bounds);
   a.alm = alm;
   a.phase_out = phase;
+  if (block_out) {
+    a.use_blk_out = 1;
+    for (int b = 0; b < nblk; ++b) a.blk_out[b] = block_out[b];
+  }
   if (legendre_gen(spin, ncomp, true) == 2) return hcu_legendre2_synthesis(ctx, &a, rp_bounds, spin, ncomp, legendre_nw());
   hcu_start *tab = nullptr;
   HCU_CHECK(hcu_get_start(ctx, g, c, &tab));

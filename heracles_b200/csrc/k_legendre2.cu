@@ -166,6 +166,7 @@ __device__ __forceinline__ void stage_coef2(double *cf, const LegArgs &a, i64 cb
 struct Setup2 {
   int mi, m, l0, pb, nrows, nsub;
   i64 row0, cbase, nrp_b, rp_base, poff;
+  double *out;
 };
 
 // CTA geometry, ring constants and recursion start values.  RW = ring pairs per warp, R = per CTA.
@@ -181,6 +182,7 @@ __device__ __forceinline__ bool setup2(const LegArgs &a, Setup2 &s, Chain<SPIN, 
   s.nrp_b = a.blk_rp[b + 1] - a.blk_rp[b];
   s.rp_base = a.blk_rp[b];
   s.poff = (i64)a.nm * a.ncomp * 4 * (a.blk_rp[b] - a.blk_rp[0]);
+  s.out = a.use_blk_out ? a.blk_out[b] : a.phase_out + s.poff;
   s.m = a.mlist ? a.mlist[s.mi] : s.mi;
   s.l0 = (SPIN == 0) ? s.m : (s.m > 2 ? s.m : 2);
   s.row0 = (i64)(g - a.grp_start[b]) * R;
@@ -535,7 +537,7 @@ __global__ void __launch_bounds__(32 * NW, 1) legendre_synthesis2_kernel(LegArgs
   Chain<SPIN, true> ch;
   bool alive;
   const bool active = setup2<SPIN, NW, true>(a, st, ch, alive, warp, lane);
-  double *dst = a.phase_out + st.poff + ((i64)st.mi * st.nrp_b + st.row0) * a.ncomp * 4;
+  double *dst = st.out + ((i64)st.mi * st.nrp_b + st.row0) * a.ncomp * 4;
   if (!active) {  // every output row must be defined
     for (int i = threadIdx.x; i < st.nrows * a.ncomp * 4; i += K::NT) dst[i] = 0.0;
     return;

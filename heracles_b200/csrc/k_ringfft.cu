@@ -295,13 +295,13 @@ __device__ __forceinline__ double2 cap_combine(const double2 *Yr, int i, int k) 
   return z;
 }
 
-__device__ __forceinline__ void store_phase(double *phase, i64 idx, double2 n,
+__device__ __forceinline__ void store_phase(double *o4, double2 n,
                                             double2 s, double2 ph, double w) {
   double2 p = make_double2((n.x + s.x) * w, (n.y + s.y) * w);
   double2 q = make_double2((n.x - s.x) * w, (n.y - s.y) * w);
   p = cmul(p, ph);
   q = cmul(q, ph);
-  double4 *o = reinterpret_cast<double4 *>(phase + idx * 4);
+  double4 *o = reinterpret_cast<double4 *>(o4);
   *o = make_double4(p.x, p.y, q.x, q.y);
 }
 
@@ -309,7 +309,7 @@ __device__ __forceinline__ void store_phase(double *phase, i64 idx, double2 n,
 __global__ void cap_post_kernel(i64 nside, int nm, const int32_t *mlist, int ncomp,
                                 const double2 *Y, i64 ncap, const double *ring_weights,
                                 i64 rp_lo, i64 nrp_local, i64 rp_first,
-                                double *phase) {
+                                double *phase, const hcu_rowdest dest) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= nm) return;
   const int m = mlist ? mlist[row] : row;
@@ -331,15 +331,14 @@ __global__ void cap_post_kernel(i64 nside, int nm, const int32_t *mlist, int nco
              (12.0 * (double)nside * (double)nside);
   if (ring_weights) w *= ring_weights[rp];
   double2 ph = expmipi((double)m / (4.0 * (double)i));
-  i64 idx = ((i64)row * nrp_local + (rp - rp_lo)) * ncomp + comp;
-  store_phase(phase, idx, xn, xs, ph, w);
+  store_phase(hcu_row_ptr(dest, phase, row, nrp_local * ncomp * 4) + ((rp - rp_lo) * ncomp + comp) * 4, xn, xs, ph, w);
 }
 
 // belt: X[rb][k], rb = ring - nside (0..2 nside), k = 0..2 nside
 __global__ void belt_post_kernel(i64 nside, int nm, const int32_t *mlist, int ncomp, int comp,
                                  const double2 *X, const double *ring_weights,
                                  i64 rp_lo, i64 nrp_local, i64 rp_first,
-                                 double *phase) {
+                                 double *phase, const hcu_rowdest dest) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= nm) return;
   const int m = mlist ? mlist[row] : row;
@@ -363,8 +362,7 @@ __global__ void belt_post_kernel(i64 nside, int nm, const int32_t *mlist, int nc
   if (ring_weights) w *= ring_weights[rp];
   double2 ph = make_double2(1., 0.);
   if (((i - nside) & 1) == 0) ph = expmipi((double)m / (4.0 * (double)nside));
-  i64 idx = ((i64)row * nrp_local + (rp - rp_lo)) * ncomp + comp;
-  store_phase(phase, idx, xn, xs, ph, w);
+  store_phase(hcu_row_ptr(dest, phase, row, nrp_local * ncomp * 4) + ((rp - rp_lo) * ncomp + comp) * 4, xn, xs, ph, w);
 }
 
 // ---------------------------------------------------------------------------
@@ -660,7 +658,7 @@ static i64 cap_stride(i64 imax) { return 2 * imax * (imax + 1); }
 // first-generation cap transforms of ring pairs [lo, hi): sub-FFTs into Y, then the post kernel
 static int old_caps_forward(hcu_ctx *ctx, hcu_geom *g, int ncomp, const hcu_ptrs &maps, const double *ring_weights,
                             i64 rp_lo, i64 nrp_local, i64 lo, i64 hi, const int32_t *mlist, int nm, double *phase,
-                            i64 ystride) {
+                            i64 ystride, const hcu_rowdest &dest) {
   if (lo >= hi) return HCU_OK;
   const i64 nside = g->nside;
   const int mthreads = 128;
@@ -690,7 +688,7 @@ static int old_caps_forward(hcu_ctx *ctx, hcu_geom *g, int ncomp, const hcu_ptrs
   }
   dim3 grid(mblocks, (unsigned)(hi - lo), (unsigned)ncomp);
   cap_post_kernel<<<grid, mthreads, 0, ctx->stream>>>(nside, nm, mlist, ncomp, Y, ystride, ring_weights, rp_lo,
-                                                      nrp_local, lo, phase);
+                                                      nrp_local, lo, phase, dest);
   HCU_LAUNCH_CHECK(ctx);
   return HCU_OK;
 }
@@ -761,7 +759,10 @@ static cap_split split_caps(const hcu_geom *g, i64 cap_lo, i64 cap_hi) {
 // forward ring FFT stage for ring pairs [rp_lo, rp_hi) of ncomp maps; phase rows follow mlist (nm rows)
 int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
                          const hcu_ptrs &maps, const double *ring_weights,
-                         i64 rp_lo, i64 rp_hi, const int32_t *mlist, int nm, double *phase) {
+                         i64 rp_lo, i64 rp_hi, const int32_t *mlist, int nm, double *phase,
+                         const hcu_rowdest *destp) {
+  hcu_rowdest dest;
+  if (destp) dest = *destp;
   const i64 nside = g->nside;
   const i64 ncap = 2 * nside * (nside - 1);
   const i64 nrp_local = rp_hi - rp_lo;
@@ -777,18 +778,18 @@ int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
     const cap_split cs = split_caps(g, cap_lo, cap_hi);
     if (cs.ystride) HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_cap, sizeof(double2) * (size_t)cs.ystride * ncomp));
     HCU_CHECK(old_caps_forward(ctx, g, ncomp, maps, ring_weights, rp_lo, nrp_local, cs.b_lo, cs.b_hi, mlist, nm,
-                               phase, cs.ystride));
+                               phase, cs.ystride, dest));
     HCU_CHECK(hcu_ring2_run(ctx, g, false, false, lmax, ncomp, maps, ring_weights, rp_lo, nrp_local, cs.n_lo, cs.n_hi,
-                            mlist, nm, nullptr, phase));
+                            mlist, nm, nullptr, phase, &dest));
     HCU_CHECK(old_caps_forward(ctx, g, ncomp, maps, ring_weights, rp_lo, nrp_local, cs.a_lo, cs.a_hi, mlist, nm,
-                               phase, cs.ystride));
+                               phase, cs.ystride, dest));
   }
 
   // ---- equatorial belt: ring pairs rp >= nside - 1 -------------------------------
   i64 belt_lo = rp_lo > nside - 1 ? rp_lo : nside - 1, belt_hi = rp_hi;
   if (belt_lo < belt_hi && g->r2_belt) {
     HCU_CHECK(hcu_ring2_run(ctx, g, false, true, lmax, ncomp, maps, ring_weights, rp_lo, nrp_local, belt_lo, belt_hi,
-                            mlist, nm, nullptr, phase));
+                            mlist, nm, nullptr, phase, &dest));
   } else if (belt_lo < belt_hi) {
     HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_belt, sizeof(double2) * (size_t)nk * (2 * nside + 1)));
     double2 *X = (double2 *)ctx->ws_belt.ptr;
@@ -804,7 +805,7 @@ int hcu_ring_fft_forward(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp,
       }
       dim3 grid(mblocks, (unsigned)(belt_hi - belt_lo));
       belt_post_kernel<<<grid, mthreads, 0, ctx->stream>>>(
-          nside, nm, mlist, ncomp, c, X, ring_weights, rp_lo, nrp_local, belt_lo, phase);
+          nside, nm, mlist, ncomp, c, X, ring_weights, rp_lo, nrp_local, belt_lo, phase, dest);
       HCU_LAUNCH_CHECK(ctx);
     }
   }

@@ -236,6 +236,7 @@ struct R2Args {
   const double *rw;
   i64 rp_lo, nrp_local;
   double *phase;
+  hcu_rowdest dest;  // forward: where the rows go (nd == 0: phase)
 };
 
 // floor(x / d) for 0 <= x < 2^23, d >= 1, through the float reciprocal (one correction step)
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(512, 1) ring2_kernel(const R2Args A) {
       // untangle N / S, fold to the rows of this launch, ring phase and quadrature weight
       double w = 4.0 * 3.141592653589793238462643383279502884197 / (double)A.npix;
       if (A.rw) w *= A.rw[rp];
-      double *out = A.phase + ((rp - A.rp_lo) * A.ncomp + c) * 4;
+      const i64 ooff = ((rp - A.rp_lo) * A.ncomp + c) * 4;
       const i64 rstride = A.nrp_local * A.ncomp * 4;
       const int nm = A.nm;
       auto zaddr = [&](int k) {  // where Z[k] waits in the scratch
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(512, 1) ring2_kernel(const R2Args A) {
         const double2 xs = make_double2(0.5 * d.y, -0.5 * d.x);
         const double2 pp = cmul(make_double2((xn.x + xs.x) * w, (xn.y + xs.y) * w), ph);
         const double2 qq = cmul(make_double2((xn.x - xs.x) * w, (xn.y - xs.y) * w), ph);
-        stcs4(out + (i64)row * rstride, make_double4(pp.x, pp.y, qq.x, qq.y));
+        stcs4(hcu_row_ptr(A.dest, A.phase, row, rstride) + ooff, make_double4(pp.x, pp.y, qq.x, qq.y));
       };
       // two rows in flight per thread; the second is clamped for its loads and dropped at the store
       for (int row0 = tid; row0 < nm; row0 += 2 * NT) {
@@ -681,7 +682,7 @@ void hcu_ring2_free(hcu_geom *g) {
 // inverse == false: maps -> phase rows (mlist, nm), inverse == true: phase rows (mpos) -> maps
 int hcu_ring2_run(hcu_ctx *ctx, hcu_geom *g, bool inverse, bool belt, int lmax, int ncomp, const hcu_ptrs &maps,
                   const double *ring_weights, i64 rp_lo, i64 nrp_local, i64 rp_a, i64 rp_b, const int32_t *mlist,
-                  int nm, const int32_t *mpos, double *phase) {
+                  int nm, const int32_t *mpos, double *phase, const hcu_rowdest *dest) {
   if (rp_a >= rp_b) return HCU_OK;
   const int nside = (int)g->nside;
   R2Args A;
@@ -703,6 +704,7 @@ int hcu_ring2_run(hcu_ctx *ctx, hcu_geom *g, bool inverse, bool belt, int lmax, 
   A.rp_lo = rp_lo;
   A.nrp_local = nrp_local;
   A.phase = phase;
+  if (dest) A.dest = *dest;
   for (int p = 0; p < 14; ++p) A.tw_off[p] = g->r2_tw_off[p];
   A.tw = g->r2_tw;
   if (belt) {

@@ -179,7 +179,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, int parity) {
   }
 }
 
-#define HCU_MAX_BLOCKS 16
 struct LegArgs {
   int lmax, nm, ncomp;      // ncomp: components present in `phase` rows (<= capacity of the template)
   const int *mlist;         // nullptr: m = index
@@ -202,6 +201,10 @@ struct LegArgs {
   int st_nrp;
   hcu_ptrs alm;             // one complex128 row per component
   double *phase_out;        // synthesis output, same layout as `phase` with (reN, imN, reS, imS)
+  // multi-GPU: block b of the synthesis output is written to blk_out[b] (the peer that owns those ring pairs) instead of
+  // phase_out + its offset in the concatenation
+  int use_blk_out;
+  double *blk_out[HCU_MAX_BLOCKS];
   double *work;             // [2] counters
 };
 

@@ -27,7 +27,9 @@ stand-in that evaluates the stages with the oracle.
 
 from __future__ import annotations
 
+import ctypes
 import hashlib
+import os
 
 import numpy as np
 
@@ -40,11 +42,12 @@ __all__ = ["ShardPlan", "StagedKernels", "Lane", "make_lanes", "DistributedTrans
 class ShardPlan:
     """which ring pairs and which m every rank owns"""
 
-    def __init__(self, nside: int, lmax: int, world: int, fft_cost=(3.08e-6, 0.0584, 3.39e-6), align: int = 256):
-        """fft_cost = (a, b, c): relative ring-FFT cost of a ring pair, a * M log2 M + b for a polar-cap
-        pair (M = power-of-two Bluestein length of its 4 sub-FFTs) and c * pixels for a belt pair (cuFFT).
-        Fitted (rms 3 %) to the per-rank FFT stage times of an 8-GPU C4 run (profiles/): small cap rings
-        are dominated by the per-ring term.  The ring-pair blocks are balanced by this cost;
+    def __init__(self, nside: int, lmax: int, world: int, fft_cost=(1.52e-6, 0.041, 3.39e-6), align: int = 256):
+        """fft_cost = (a, b, c): relative ring-FFT cost of a ring pair, a * M log2 M + b * nside / 4096 for a polar-cap
+        pair (M = power-of-two Bluestein length of its 4 sub-FFTs; the second term is the emission of its lmax + 1 phase
+        rows, the same for every ring) and c * pixels for a belt pair.  Fitted to the launch times of the fused ring-FFT
+        kernels at nside 4096 (k_ringfft2.cu; profiles/r02_fft2_launches.txt): Bluestein rings of length 8192 cost 1.8 x a
+        belt pair, the rings below it 0.8 x on average.  The ring-pair blocks are balanced by this cost;
         fft_cost=None balances by pixel count.  The boundaries are then snapped to multiples of `align` ring pairs, the
         ring-pair group one Legendre CTA works on: a block of 1454 ring pairs costs six CTAs per m, the last one two thirds
         full -- measured at C4 on 8 GPUs, unaligned blocks made 34 instead of 32 groups and the Legendre stage 5.5 % slower,
@@ -66,7 +69,7 @@ class ShardPlan:
         else:
             a, b, c = fft_cost
             m = 2.0 ** np.ceil(np.log2(np.maximum(2 * i - 1, 2)))
-            npair = np.where(i < nside, a * m * np.log2(m) + b, c * 8.0 * nside)
+            npair = np.where(i < nside, a * m * np.log2(m) + b * nside / 4096.0, c * 8.0 * nside)
             npair[-1] = c * 4.0 * nside
         cum = np.concatenate([[0], np.cumsum(npair)])
         bounds = [0]
@@ -207,6 +210,25 @@ class StagedKernels:
         self._check(self.ctx.lib.hcu_phase2map(self.ctx.handle, self.nside, self.lmax, nb, phase.data_ptr(), self._p(mpos),
                                                rp_lo, rp_hi, maps.data_ptr(), maps.stride(0)))
 
+    def map2phase_peers(self, maps, rp_lo, rp_hi, mlist, row_start, dest_ptrs):
+        """hcu_map2phase whose rows [row_start[d], row_start[d+1]) are written to the (peer) address dest_ptrs[d]"""
+        import ctypes
+
+        nb, nd = maps.shape[0], len(dest_ptrs)
+        rs = (ctypes.c_int32 * (nd + 1))(*row_start)
+        bp = (ctypes.c_void_p * nd)(*dest_ptrs)
+        self._check(self.ctx.lib.hcu_map2phase_peers(self.ctx.handle, self.nside, self.lmax, nb, maps.data_ptr(), maps.stride(0),
+                                                     None, rp_lo, rp_hi, self._p(mlist), mlist.numel(), nd, rs, bp))
+
+    def alm2phase_peers(self, alm, spin, nb, mlist, rp_bounds, block_ptrs):
+        """hcu_alm2phase_blocks whose block b is written to the (peer) address block_ptrs[b]"""
+        import ctypes
+
+        rb = (ctypes.c_int64 * len(rp_bounds))(*rp_bounds)
+        bp = (ctypes.c_void_p * len(block_ptrs))(*block_ptrs)
+        self._check(self.ctx.lib.hcu_alm2phase_peers(self.ctx.handle, self.nside, self.lmax, spin, nb, alm.data_ptr(),
+                                                     alm.stride(0), self._p(mlist), mlist.numel(), len(rp_bounds) - 1, rb, bp))
+
     def sync_streams(self):
         """make the library's stream the caller's current torch stream"""
         import torch
@@ -214,6 +236,115 @@ class StagedKernels:
         # torch's default stream has handle 0, which hcu_set_stream reads as "the context's own
         # stream": name the legacy default stream explicitly (cudaStreamLegacy = 1)
         self.ctx.set_stream(torch.cuda.current_stream().cuda_stream or 1)
+
+
+# ---------------------------------------------------------------------------------------
+# exchange through peer memory
+# ---------------------------------------------------------------------------------------
+class PeerExchange:
+    """
+    The ring-block <-> m-distributed exchange WITHOUT a collective: every rank owns a double-buffered phase array in
+    device memory that all other ranks of the node have opened over CUDA IPC, and the PRODUCING kernels (the ring FFT's
+    row emission, the Legendre synthesis' flush) write every row straight into the buffer of the rank that consumes it
+    -- NVLink peer stores instead of a send buffer + ``all_to_all_single`` + a receive buffer.
+
+    (The analysis direction stages the rows of the OTHER ranks locally and pushes them as one contiguous copy-engine
+    copy per destination, ``push``: scattered 32-byte stores over NVLink reach a fraction of the link rate; the
+    synthesis direction's Legendre kernel is compute-bound and stores remotely for free.)
+
+    Ordering: stage n uses half n % 2 of every buffer and ends with one (stream-ordered, 1-element) all-reduce.  A rank
+    leaves that barrier only after every rank's producer kernel of stage n has completed, so the consumer may read; and
+    a producer of stage n + 2 starts only after the barrier of stage n + 1, which every rank enters after ITS consumer
+    of stage n -- so no half is overwritten while it is still being read.
+    """
+
+    PER_MAX = 48  # doubles per (m, ring pair): 12 components x 4
+
+    def __init__(self, ctx, plan, rank, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        self.ctx, self.plan, self.rank, self.group = ctx, plan, int(rank), group
+        self.device = device
+        W = plan.world
+        lo, hi = plan.rp_range(rank)
+        n_ana = len(plan.mlists[rank]) * plan.nrp * self.PER_MAX      # what the Legendre analysis of this rank reads
+        n_syn = (plan.lmax + 1) * (hi - lo) * self.PER_MAX             # what the inverse ring FFTs of this rank read
+        self.half_elems = max(n_ana, n_syn, 1)
+        self.base = ctx.malloc_device(2 * self.half_elems * 8)
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(ctx.lib.hcu_ipc_export(ctx.handle, ctypes.c_void_p(self.base), handle))
+        mine = (bytes(handle), self.half_elems)
+        everyone = [None] * W
+        dist.all_gather_object(everyone, mine, group=group)
+        self.ptr, self._opened = [], []
+        for d, (h, n) in enumerate(everyone):
+            if d == rank:
+                b = self.base
+            else:
+                p = ctypes.c_void_p()
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                _lib.check(ctx.lib.hcu_ipc_open(ctx.handle, buf, ctypes.byref(p)))
+                b = p.value
+                self._opened.append(b)
+            self.ptr.append((b, b + 8 * n))
+        self.stage = 0
+        self.flag = torch.zeros(1, dtype=torch.float32, device=device)
+        dist.barrier(group=group)  # every rank has opened every buffer before anybody writes
+
+    def next_half(self) -> int:
+        h = self.stage & 1
+        self.stage += 1
+        return h
+
+    def barrier(self):
+        """stream-ordered: everything queued on the current stream so far, on every rank, precedes what follows"""
+        import torch.distributed as dist
+
+        dist.all_reduce(self.flag, group=self.group)
+
+    def push(self, src, chunks):
+        """copy-engine pushes: chunks = [(rank, offset in src, elements, destination address)]; the copies run on a few
+        side streams (ordered after what the current stream has queued) and the current stream waits for them"""
+        import torch
+
+        if not chunks:
+            return
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_copy_streams"):
+            self._copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(4)]
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        used = []
+        for i, (d, off, n, addr) in enumerate(chunks):
+            st = self._copy_streams[i % len(self._copy_streams)]
+            if st not in used:
+                st.wait_event(ev)
+                used.append(st)
+            dst = torch.as_tensor(_CudaView(addr, (n,), "<f8"), device=self.device)
+            with torch.cuda.stream(st):
+                dst.copy_(src[off:off + n], non_blocking=True)
+        for st in used:
+            done = torch.cuda.Event()
+            done.record(st)
+            cur.wait_event(done)
+
+    def local(self, half: int, n: int):
+        """torch view of the first n doubles of one half of this rank's buffer"""
+        import torch
+
+        return torch.as_tensor(_CudaView(self.ptr[self.rank][half], (n,), "<f8"), device=self.device)
+
+    def close(self):
+        if self.base:
+            self.ctx.synchronize()
+            for p in self._opened:
+                self.ctx.lib.hcu_ipc_close(self.ctx.handle, ctypes.c_void_p(p))
+            self._opened = []
+            self.ctx.free(self.base)
+            self.base = 0
 
 
 # ---------------------------------------------------------------------------------------
@@ -227,8 +358,9 @@ class Lane:
     batch is in its (FP64-bound) Legendre kernels.
     """
 
-    def __init__(self, kernels, group=None, stream=None):
+    def __init__(self, kernels, group=None, stream=None, peers=None):
         self.k, self.group, self.stream = kernels, group, stream
+        self.peers = peers  # PeerExchange: the producing kernels write into the consumers' buffers (no all-to-all)
         self.ws = {}
 
     def context(self):
@@ -314,6 +446,9 @@ class DistributedTransform:
         self._ws.clear()
         for lane in self.lanes:
             lane.ws.clear()
+            if lane.peers is not None:
+                lane.peers.close()
+                lane.peers = None
 
     def _all_to_all(self, lane, out, inp, out_splits, in_splits):
         import torch.distributed as dist
@@ -332,16 +467,40 @@ class DistributedTransform:
         lo, hi = plan.rp_range(g)
         nrp_me, nm_me = hi - lo, len(plan.mlists[g])
         per = nb * 4
-        send = self._buf(lane, "send", (plan.lmax + 1) * nrp_me * per)
-        with self._mark("fft"):
-            k.map2phase(maps, lo, hi, self.m_all, send)
-        yield
         in_splits = [len(plan.mlists[d]) * nrp_me * per for d in range(W)]
         out_splits = [nm_me * plan.nrp_of(s) * per for s in range(W)]
-        recv = self._buf(lane, "recv", sum(out_splits))
-        with self._mark("a2a"):
-            self._all_to_all(lane, recv, send, out_splits, in_splits)
-        yield
+        if lane.peers is not None:
+            # Rows of destination d belong in MY block of d's blocked phase array (behind the blocks of the ranks before
+            # me).  My own rows are written there by the kernel; the others are emitted into a local staging array
+            # (scattered 32-byte stores over NVLink run at a fraction of the link rate -- measured, profiles/) and
+            # pushed as ONE contiguous copy per destination by the copy engines: no SM, no collective.
+            ex = lane.peers
+            half = ex.next_half()
+            before = sum(plan.nrp_of(s) for s in range(g))
+            row_start = [0]
+            for d in range(W):
+                row_start.append(row_start[-1] + len(plan.mlists[d]))
+            send = self._buf(lane, "send", (plan.lmax + 1) * nrp_me * per)
+            target = [ex.ptr[d][half] + 8 * len(plan.mlists[d]) * before * per for d in range(W)]
+            dest = [target[d] if d == g else send.data_ptr() + 8 * row_start[d] * nrp_me * per for d in range(W)]
+            with self._mark("fft"):
+                k.map2phase_peers(maps, lo, hi, self.m_all, row_start, dest)
+            yield
+            with self._mark("a2a"):
+                ex.push(send, [(d, row_start[d] * nrp_me * per, in_splits[d], target[d]) for d in range(W) if d != g and in_splits[d]])
+                ex.barrier()
+            self.exchanged_bytes += 8 * (sum(in_splits) - in_splits[g])
+            recv = ex.local(half, sum(out_splits))
+            yield
+        else:
+            send = self._buf(lane, "send", (plan.lmax + 1) * nrp_me * per)
+            with self._mark("fft"):
+                k.map2phase(maps, lo, hi, self.m_all, send)
+            yield
+            recv = self._buf(lane, "recv", sum(out_splits))
+            with self._mark("a2a"):
+                self._all_to_all(lane, recv, send, out_splits, in_splits)
+            yield
         off = 0
         with self._mark("leg_ana"):
             if nm_me and hasattr(k, "phase2alm_blocks") and W <= 16:
@@ -364,6 +523,25 @@ class DistributedTransform:
         per = nb * 4
         in_splits = [nm_me * plan.nrp_of(d) * per for d in range(W)]
         out_splits = [len(plan.mlists[s]) * nrp_me * per for s in range(W)]
+        if lane.peers is not None:
+            # my rows of destination d's phase array start behind the rows of the ranks before me
+            ex = lane.peers
+            half = ex.next_half()
+            rows_before = sum(len(plan.mlists[s]) for s in range(g))
+            blocks = [ex.ptr[d][half] + 8 * rows_before * plan.nrp_of(d) * per for d in range(W)]
+            with self._mark("leg_syn"):
+                if nm_me:
+                    k.alm2phase_peers(alm, spin, nb, self.mlist_me, list(plan.rp_bounds), blocks)
+            yield
+            with self._mark("a2a"):
+                ex.barrier()
+            self.exchanged_bytes += 8 * (sum(in_splits) - in_splits[g])
+            recv = ex.local(half, sum(out_splits))
+            yield
+            with self._mark("ifft"):
+                k.phase2map(recv, nb, self.mpos, lo, hi, maps)
+            yield
+            return
         send = self._buf(lane, "send", sum(in_splits))
         off = 0
         with self._mark("leg_syn"):
@@ -482,6 +660,44 @@ class DistributedTransform:
             t = torch.from_numpy(full).to(self.device).to(torch.complex128)
             self._ws[key] = t
         return t
+
+
+def exchange_mode() -> str:
+    """HCU_DIST_EXCHANGE = peer (default: producer kernels write into the consumers' buffers over NVLink peer memory)
+    or nccl (send buffer + all_to_all_single + receive buffer)"""
+    mode = os.environ.get("HCU_DIST_EXCHANGE", "peer").lower()
+    if mode not in ("peer", "nccl"):
+        msg = f"HCU_DIST_EXCHANGE must be 'peer' or 'nccl', not {mode!r}"
+        raise ValueError(msg)
+    return mode
+
+
+def attach_peers(lanes, ctx_of, plan, rank, device):
+    """give every lane a PeerExchange (all ranks call this in the same order); on failure (no IPC between the ranks'
+    devices) every rank falls back to the NCCL exchange together"""
+    import warnings
+
+    import torch
+    import torch.distributed as dist
+
+    if plan.world <= 1 or exchange_mode() != "peer":
+        return lanes
+    for lane in lanes:
+        ex, ok = None, 1
+        try:
+            ex = PeerExchange(ctx_of(lane), plan, rank, group=lane.group, device=device)
+        except Exception as e:  # noqa: BLE001 - reported below, on every rank
+            ok, err = 0, e
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=lane.group)
+        if int(flag.item()) == 1:
+            lane.peers = ex
+        else:
+            if ex is not None:
+                ex.close()
+            if not ok:
+                warnings.warn(f"peer-memory exchange unavailable ({err}); using the NCCL all-to-all", stacklevel=2)
+    return lanes
 
 
 def make_lanes(ctx, nside, lmax, n=2, group=None):
@@ -618,6 +834,8 @@ class DistributedPipeline:
         # another.  Measured (profiles/r02_lanes_c3_n2.txt): no gain -- a Legendre CTA takes a whole SM (all registers,
         # 205 KB of shared memory), so the second lane's kernels time-slice the SMs instead of sharing them; default 1.
         lanes = make_lanes(self.ctx, mapper.nside, mapper.lmax, lanes if self.world > 1 else 1, group=group)
+        # the exchange goes through NVLink peer memory unless HCU_DIST_EXCHANGE=nccl (or IPC is unavailable)
+        attach_peers(lanes, lambda lane: lane.k.ctx, self.plan, self.rank, self.device)
         self.kernels = lanes[0].k
         self.transform = DistributedTransform(self.kernels, self.plan, self.rank, group=group, niter=mapper.niter,
                                               device=self.device, lanes=lanes)

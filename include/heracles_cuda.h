@@ -211,6 +211,26 @@ int hcu_alm2phase_blocks(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int nc
 int hcu_phase2map(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp, const double *phase,
                   const int32_t *mpos, int64_t rp_lo, int64_t rp_hi, double *maps,
                   int64_t map_stride);
+/* The exchange between the ring-distributed and the m-distributed stage WITHOUT a collective: the producing kernel
+ * writes every row straight into the buffer of the rank that consumes it, over NVLink peer memory (the reference is a
+ * single process, heracles/healpy.py:183-189; north_star's "all-to-all to an m-distributed Legendre stage").
+ *   hcu_map2phase_peers  hcu_map2phase whose rows [row_start[d], row_start[d+1]) -- the m owned by rank d -- go to
+ *                        dest_base[d] + ((row - row_start[d]) * (rp_hi - rp_lo) + rp - rp_lo) * ncomp * 4, i.e. into
+ *                        this rank's block of rank d's blocked phase array (the layout hcu_phase2alm_blocks reads).
+ *   hcu_alm2phase_peers  hcu_alm2phase_blocks whose block b is written to block_out[b]: this rank's rows of rank
+ *                        b's phase array (the layout hcu_phase2map reads).
+ *   hcu_ipc_export / hcu_ipc_open / hcu_ipc_close  share a hcu_malloc_device buffer with the other processes of the
+ *                        node (cudaIpc*; handle64 is an opaque 64-byte token). */
+int hcu_map2phase_peers(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp, const double *maps,
+                        int64_t map_stride, const double *ring_weights, int64_t rp_lo, int64_t rp_hi,
+                        const int32_t *mlist, int nm, int ndest, const int32_t *row_start,
+                        double *const *dest_base);
+int hcu_alm2phase_peers(hcu_ctx *ctx, int64_t nside, int lmax, int spin, int ncomp, const void *alm,
+                        int64_t alm_stride, const int32_t *mlist, int nm, int nblocks,
+                        const int64_t *rp_bounds, double *const *block_out);
+int hcu_ipc_export(hcu_ctx *ctx, const void *ptr, void *handle64);
+int hcu_ipc_open(hcu_ctx *ctx, const void *handle64, void **ptr);
+int hcu_ipc_close(hcu_ctx *ctx, void *ptr);
 
 /* ---- alm -> Cl ------------------------------------------------------------ */
 /* alm2cl(alm, alm2, lmax=lmax) -- heracles/twopoint.py:63-101, as a block:

@@ -118,3 +118,28 @@ def test_distributed_transform_world1(hb, ctx, oracle, spin):
     ref = oracle.almxfl(oracle.map2alm(nside, lmax, full, spin=spin, niter=niter), fl)
     for c in range(nb):
         assert relerr(alm[c].cpu().numpy(), ref[c]) < TOL
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_memory_exchange_between_processes(world):
+    """The exchange of the multi-GPU path without a collective: `world` PROCESSES (here sharing one GPU, gloo for the
+    barrier) open each other's phase buffers over CUDA IPC; the ring-FFT emission and the Legendre-synthesis flush
+    write their rows straight into the consumer's buffer (hcu_map2phase_peers / hcu_alm2phase_peers).  The spectra of
+    3 spin-0 maps + 5 spin-2 fields, niter 3, must match the single-process transform (tools/dist_check.py)."""
+    import os
+    import socket
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py"), "--nside", "64", "--niter", "3",
+           "--backend", "gloo", "--same-device"]
+    env = dict(os.environ, HCU_DIST_EXCHANGE="peer", OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    text = out.stdout + out.stderr
+    assert out.returncode == 0 and "-> OK" in text and "through peer memory" in text, text[-3000:]

@@ -18,10 +18,17 @@ from heracles_b200.dist import DistributedPipeline
 ap = argparse.ArgumentParser()
 ap.add_argument("--nside", type=int, default=256)
 ap.add_argument("--niter", type=int, default=3)
+ap.add_argument("--backend", default="nccl", help="gloo: host collectives (with --same-device the ranks can share one GPU)")
+ap.add_argument("--same-device", action="store_true", help="every rank on cuda:0 (peer-memory exchange between processes of one GPU)")
 args = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+if args.same_device:
+    local = 0
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if args.backend == "nccl":
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+else:
+    dist.init_process_group(args.backend)
 nside, lmax = args.nside, 2 * args.nside
 mapper = hb.CudaHealpixMapper(nside, lmax, deconvolve=False, niter=args.niter, device=local)
 npix = 12 * nside * nside
@@ -57,6 +64,7 @@ if rank == 0:
             err = max(err, float(np.max(np.abs(cl[i, j] - ref[i, j]) / np.sqrt(np.abs(auto[i] * auto[j]) + 1e-300))))
     ok = err < 1e-10
     print(f"dist_check world={world} nside={nside} niter={args.niter}: max |dCl| / sqrt(Cl_ii Cl_jj) = {err:.3e} -> {'OK' if ok else 'FAIL'}; "
-          f"exchanged {dp.transform.exchanged_bytes / 1e6:.1f} MB per rank")
+          f"exchanged {dp.transform.exchanged_bytes / 1e6:.1f} MB per rank through "
+          f"{'peer memory' if dp.transform.lanes[0].peers is not None else 'nccl all-to-all'}")
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
