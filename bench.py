@@ -450,7 +450,13 @@ class Pipeline:
         else:
             vis = mapper.create()
             vis += 1.0
+        # finished maps are transformed on a second library context while the next bins are still being mapped (the
+        # mapping is PCIe-bound, the transform FP64-bound); HCU_BENCH_OVERLAP=0: map everything, then transform
+        ov = None
+        if not dist_mode and os.environ.get("HCU_BENCH_OVERLAP", "1") != "0":
+            ov = hb.OverlappedTransform(mapper)
         pos = she = None
+        stats = mapper.new_page_stats()  # one accumulator, cleared per bin: a cudaFree per bin would wait for the whole device
         for b in range(self.nbins):
             hc = self.hcat[b]
             if dist_mode and pos is not None:
@@ -462,7 +468,7 @@ class Pipeline:
             else:
                 pos = mapper.create(spin=0)
                 she = mapper.create(2, spin=2) if cfg["she"] else None
-            stats = mapper.new_page_stats()
+            stats *= 0.0
             for p in self.my_pages():
                 j = self.hidx[p % self.pool]
                 lon, lat, w = hc["lon"][j], hc["lat"][j], hc["w"][j]
@@ -488,6 +494,11 @@ class Pipeline:
                     dp.put(2, b, she)
                 continue
             pos -= vis
+            if ov is not None:
+                ov.submit(("POS", b), pos, spin=0)
+                if she is not None:
+                    ov.submit(("SHE", b), she, spin=2)
+                continue
             maps["POS", b] = pos
             if she is not None:
                 maps["SHE", b] = she
@@ -510,7 +521,7 @@ class Pipeline:
             if self.rank == 0 and os.environ.get("HCU_BENCH_VERBOSE"):
                 print(f"e2e rank 0: mapping {t_map:.3f} s, reduce + transform + Cl {dt - t_map:.3f} s", file=sys.stderr, flush=True)
             return dt, h2d, d2h, checksum, ncl
-        alms = hb.transform(fields, maps)
+        alms = ov.finish() if ov is not None else hb.transform(fields, maps)
         for (k, i), a in alms.items():
             hb.update_metadata(a, spin=0 if k == "POS" else 2)
         cls = hb.angular_power_spectra(alms, debias=False)
@@ -1050,7 +1061,9 @@ def main():
             tt = float(t.item())
         api = ("CudaHealpixMapper.map_page(sync=False) + heracles_b200.dist.DistributedPipeline.spectra, pinned host pages"
                if world > 1 else
-               "CudaHealpixMapper.map_page(sync=False) + heracles_b200.transform + angular_power_spectra, pinned host pages")
+               "CudaHealpixMapper.map_page(sync=False) + heracles_b200." + ("transform" if os.environ.get("HCU_BENCH_OVERLAP", "1") == "0"
+                                                                            else "OverlappedTransform (transforms of finished bins beside the mapping of the next)")
+               + " + angular_power_spectra, pinned host pages")
         line["e2e"] = {"value": tt / max(1, args.e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(res[1]),
                        "d2h_bytes_per_step": int(res[2]), "spectra": res[4], "checksum": res[3], "api": api}
 

@@ -8,6 +8,7 @@ Public surface (mirrors the reference interfaces of this path):
   CudaHealpixMapper            <- heracles.healpy.HealpixMapper
   alm2cl, angular_power_spectra <- heracles.twopoint
   transform                    <- heracles.mapping.transform (batched over maps)
+  OverlappedTransform          the same transforms, run beside the catalogue mapping (second context + stream)
   dices.region_alms, dices.jackknife_cls <- heracles.dices.jackknife (batched region transforms)
 
 There is no CPU fallback: importing the kernels' library fails loudly if
@@ -20,6 +21,7 @@ from .arrays import DeviceArray, update_metadata  # noqa: F401
 from .mapper import CudaHealpixMapper  # noqa: F401
 from .mapping import transform, transform_maps  # noqa: F401
 from .twopoint import alm2cl, alm2lmax, angular_power_spectra  # noqa: F401
+from .overlap import OverlappedTransform  # noqa: F401
 from . import dices  # noqa: F401,E402
 
 __all__ = [
@@ -27,6 +29,7 @@ __all__ = [
     "DeviceArray",
     "Context",
     "HeraclesCudaError",
+    "OverlappedTransform",
     "alm2cl",
     "alm2lmax",
     "angular_power_spectra",

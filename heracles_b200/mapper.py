@@ -167,6 +167,7 @@ class CudaHealpixMapper:
         device: int | None = None,
         sync: bool = True,
         aggregate: bool = False,
+        context: Any = None,
     ) -> None:
         if lmax is None:
             lmax = 3 * nside // 2
@@ -191,7 +192,9 @@ class CudaHealpixMapper:
         self.scheme = scheme
         self._pixwin = pixwin
         self._pixel_weights_arg = pixel_weights
-        self._ctx = _lib.get_context(device)
+        # context: a library context of its own (own stream and workspaces, _lib.extra_context) instead of the
+        # process-wide one of the device -- what lets transforms run beside the mapping (heracles_b200.overlap)
+        self._ctx = context if context is not None else _lib.get_context(device)
 
     # -- reference attributes ------------------------------------------------
     @property
