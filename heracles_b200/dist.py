@@ -445,10 +445,7 @@ class DistributedTransform:
     def release(self):
         self._ws.clear()
         for lane in self.lanes:
-            lane.ws.clear()
-            if lane.peers is not None:
-                lane.peers.close()
-                lane.peers = None
+            lane.ws.clear()  # (the peer-exchange buffers are cached per process: close_peer_exchanges())
 
     def _all_to_all(self, lane, out, inp, out_splits, in_splits):
         import torch.distributed as dist
@@ -683,21 +680,41 @@ def attach_peers(lanes, ctx_of, plan, rank, device):
     if plan.world <= 1 or exchange_mode() != "peer":
         return lanes
     for lane in lanes:
+        # Opening the peers' buffers costs tens of milliseconds per rank (cudaIpcOpenMemHandle maps gigabytes): the
+        # exchange of a (context, geometry, world, communicator) is created once per process and reused by every
+        # pipeline built later -- like the library's cached plans and workspaces.  close_peer_exchanges() frees them.
+        ctx = ctx_of(lane)
+        key = (id(ctx), plan.nside, plan.lmax, plan.world, tuple(plan.rp_bounds), int(rank), id(lane.group))
+        if key in _PEER_CACHE:
+            lane.peers = _PEER_CACHE[key]
+            continue
         ex, ok = None, 1
         try:
-            ex = PeerExchange(ctx_of(lane), plan, rank, group=lane.group, device=device)
+            ex = PeerExchange(ctx, plan, rank, group=lane.group, device=device)
         except Exception as e:  # noqa: BLE001 - reported below, on every rank
             ok, err = 0, e
         flag = torch.tensor([ok], dtype=torch.int32, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=lane.group)
         if int(flag.item()) == 1:
-            lane.peers = ex
+            lane.peers = _PEER_CACHE[key] = ex
         else:
+            _PEER_CACHE[key] = None
             if ex is not None:
                 ex.close()
             if not ok:
                 warnings.warn(f"peer-memory exchange unavailable ({err}); using the NCCL all-to-all", stacklevel=2)
     return lanes
+
+
+_PEER_CACHE: dict = {}
+
+
+def close_peer_exchanges():
+    """free the cached peer-memory exchange buffers of this process (every rank must call it)"""
+    for ex in _PEER_CACHE.values():
+        if ex is not None:
+            ex.close()
+    _PEER_CACHE.clear()
 
 
 def make_lanes(ctx, nside, lmax, n=2, group=None):
@@ -820,9 +837,12 @@ class DistributedPipeline:
     (E, B) per spin-2 field; only the upper triangle j >= i is filled).
     """
 
-    def __init__(self, mapper, npos: int = 0, nshe: int = 0, group=None, lanes: int = 1):
+    def __init__(self, mapper, npos: int = 0, nshe: int = 0, group=None, lanes: int | None = None):
         import torch
         import torch.distributed as dist
+
+        if lanes is None:
+            lanes = int(os.environ.get("HCU_DIST_LANES", "1"))
 
         self.mapper, self.group = mapper, group
         self.ctx = mapper.context
