@@ -62,6 +62,7 @@ SIGNATURES = {
     "hcu_ipc_export": (c_int, [c_vp, c_vp, c_vp]),
     "hcu_ipc_open": (c_int, [c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "hcu_ipc_close": (c_int, [c_vp, c_vp]),
+    "hcu_points2alm": (c_int, [c_vp, c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64]),
     "hcu_phase2alm": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_i64]),
     "hcu_alm2cl": (c_int, [c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_int, c_int, c_vp]),
     "hcu_alm2cl_rows": (c_int, [c_vp, c_int, ctypes.POINTER(c_vp), c_int, c_int, c_vp]),

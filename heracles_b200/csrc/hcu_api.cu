@@ -587,7 +587,7 @@ int hcu_get_coef(hcu_ctx *ctx, int lmax, int spin, hcu_coef **out) {
 
 int hcu_get_start(hcu_ctx *ctx, hcu_geom *g, hcu_coef *c, hcu_start **out) {
   *out = nullptr;
-  if (!ctx->use_start_table) return HCU_OK;
+  if (!ctx->use_start_table || g->nside <= 0) return HCU_OK;  // (nside 0: a geometry of free points, hcu_points2alm)
   auto key = std::make_pair(g->nside, std::make_pair(c->lmax, c->spin));
   auto it = ctx->start.find(key);
   if (it == ctx->start.end()) {

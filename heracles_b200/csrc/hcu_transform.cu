@@ -509,3 +509,98 @@ extern "C" int hcu_phase2map(hcu_ctx *ctx, int64_t nside, int lmax, int ncomp, c
   for (int c = 0; c < HCU_MAX_BATCH; ++c) dst.p[c] = c < ncomp ? maps + (i64)c * map_stride : nullptr;
   return hcu_ring_fft_inverse(ctx, g, lmax, ncomp, phase, mpos, rp_lo, rp_hi, dst);
 }
+
+// ---- N4: catalogue -> alm without pixels (heracles/ducc.py:92-133) ------------------------------------------------
+// ducc0.sht.adjoint_synthesis_general(map=values, spin, lmax, loc): alm_lm = sum_i v_i conj(sY_lm(theta_i, phi_i)).
+// Every point is a "ring" of its own with one sample: its ring Fourier coefficients are v exp(-i m phi), its
+// colatitude is free, and the Legendre analysis kernels (which only see cos / sin tables per ring pair) sum the
+// harmonics exactly -- O(points x lmax^2), no NUFFT: meant for the catalogue sizes the discrete mapper is used with
+// (examples/discrete.ipynb), not for 1e9 rows.
+namespace {
+__global__ void point_geom_kernel(i64 n, const double *lon, const double *lat, double *cth, double *sth, double *ch,
+                                  double *sh, double *phi) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double deg = 0.017453292519943295769;
+  const double theta = (90.0 - lat[i]) * deg;
+  double l = fmod(lon[i], 360.0);
+  if (l < 0.0) l += 360.0;  // numpy's lon % 360.0
+  phi[i] = l * deg;
+  double s, c;
+  sincos(theta, &s, &c);
+  cth[i] = c;
+  sth[i] = s;
+  sincos(0.5 * theta, &s, &c);
+  ch[i] = c;
+  sh[i] = s;
+}
+
+// phase[((m * P + pt) * ncomp + c) * 4] = v_c exp(-i m phi) as (north + south, north - south) with an empty south
+__global__ void point_phase_kernel(int P, int ncomp, const double *phi, const double *values, i64 vstride, double *phase) {
+  const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= P) return;
+  const int m = blockIdx.y;
+  double s, c;
+  sincos((double)m * phi[pt], &s, &c);
+  double4 *out = reinterpret_cast<double4 *>(phase + (((i64)m * P + pt) * ncomp) * 4);
+  for (int k = 0; k < ncomp; ++k) {
+    const double v = values[(i64)k * vstride + pt];
+    out[k] = make_double4(v * c, -v * s, v * c, -v * s);
+  }
+}
+}  // namespace
+
+extern "C" int hcu_points2alm(hcu_ctx *ctx, int lmax, int spin, int ncomp, int64_t npts, const double *lon,
+                              const double *lat, const double *values, int64_t value_stride, void *alm,
+                              int64_t alm_stride) {
+  HCU_ARG(ctx && lon && lat && values && alm, "null pointer");
+  HCU_ARG(lmax >= 0 && lmax <= 32768, "0 <= lmax <= 32768");
+  HCU_ARG(npts >= 0, "npts >= 0");
+  if (spin != 0 && spin != 2) {
+    hcu_set_error("spin-%d values not yet supported", spin);
+    return HCU_ERR_UNSUPPORTED;
+  }
+  HCU_ARG(ncomp >= 1 && ncomp <= hcu_legendre_batch(spin), "at most 12 (spin 0) / 8 (spin 2) value rows per call");
+  HCU_ARG(spin == 0 || (ncomp % 2) == 0, "spin-2 input needs (Q, U) pairs");
+  HCU_ARG(hcu_dev_accessible(alm), "alm must be device accessible (Mapper.create())");
+  if (npts == 0) return HCU_OK;
+  HCU_CUDA(cudaSetDevice(ctx->device));
+  hcu_coef *cf;
+  HCU_CHECK(hcu_get_coef(ctx, lmax, spin, &cf));
+  // device copies of the columns + the per-point geometry
+  HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_map, sizeof(double) * (size_t)npts * (size_t)(7 + ncomp)));
+  double *base = (double *)ctx->ws_map.ptr;
+  double *dlon = base, *dlat = base + npts, *cth = base + 2 * npts, *sth = base + 3 * npts, *ch = base + 4 * npts,
+         *sh = base + 5 * npts, *phi = base + 6 * npts, *dval = base + 7 * npts;
+  HCU_CUDA(cudaMemcpyAsync(dlon, lon, sizeof(double) * npts, cudaMemcpyDefault, ctx->stream));
+  HCU_CUDA(cudaMemcpyAsync(dlat, lat, sizeof(double) * npts, cudaMemcpyDefault, ctx->stream));
+  for (int k = 0; k < ncomp; ++k)
+    HCU_CUDA(cudaMemcpyAsync(dval + (i64)k * npts, values + (i64)k * value_stride, sizeof(double) * npts,
+                             cudaMemcpyDefault, ctx->stream));
+  point_geom_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, ctx->stream>>>(npts, dlon, dlat, cth, sth, ch, sh, phi);
+  HCU_LAUNCH_CHECK(ctx);
+  hcu_ptrs rows;
+  for (int c = 0; c < HCU_MAX_BATCH; ++c) rows.p[c] = c < ncomp ? (double *)alm + 2 * (i64)c * alm_stride : nullptr;
+  // chunks of points whose phase array stays below ~2 GB
+  i64 P = (i64)(2.0e9 / (32.0 * ncomp * (lmax + 1)));
+  P = std::max<i64>(256, (P / 256) * 256);
+  for (i64 p0 = 0; p0 < npts; p0 += P) {
+    const int n = (int)std::min<i64>(P, npts - p0);
+    HCU_CHECK(hcu_ws_reserve(ctx, &ctx->ws_phase, sizeof(double) * 4 * (size_t)(lmax + 1) * (size_t)n * ncomp));
+    double *phase = (double *)ctx->ws_phase.ptr;
+    dim3 grid((unsigned)((n + 127) / 128), (unsigned)(lmax + 1));
+    point_phase_kernel<<<grid, 128, 0, ctx->stream>>>(n, ncomp, phi + p0, dval + p0, npts, phase);
+    HCU_LAUNCH_CHECK(ctx);
+    hcu_geom g;  // a geometry of its own: the points of this chunk as ring pairs without a southern ring
+    g.nside = 0;
+    g.nrp = n;
+    g.cth = cth + p0;
+    g.sth = sth + p0;
+    g.ch = ch + p0;
+    g.sh = sh + p0;
+    const i64 one[2] = {0, n};
+    HCU_CHECK(hcu_legendre_analysis(ctx, &g, cf, lmax, spin, ncomp, phase, nullptr, lmax + 1, 1, one, nullptr, rows));
+  }
+  HCU_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HCU_OK;
+}

@@ -36,8 +36,9 @@ def _ptr(arr: np.ndarray) -> int:
     return arr.__array_interface__["data"][0]
 
 
-def _read_fits_table(path: str):
-    """columns of the first binary table of a FITS file as flat float64 arrays (no astropy / fitsio here)"""
+def _read_fits_table(path: str, with_header: bool = False):
+    """columns of the first binary table of a FITS file as flat float64 arrays (no astropy / fitsio here);
+    with_header: also the table's header cards as a dict"""
     with open(path, "rb") as f:
         raw = f.read()
 
@@ -62,12 +63,13 @@ def _read_fits_table(path: str):
     dts = []
     for fmt in fmts:
         rep = int(fmt[:-1] or 1)
-        code = {"D": ">f8", "E": ">f4"}[fmt[-1]]
+        code = {"D": ">f8", "E": ">f4", "J": ">i4", "K": ">i8", "I": ">i2", "B": "u1"}[fmt[-1]]
         dts.append((code, rep))
     dt = np.dtype([(f"c{i}", c, (r,)) for i, (c, r) in enumerate(dts)])
     assert dt.itemsize == rowlen
     tab = np.frombuffer(raw, dtype=dt, count=nrow, offset=off)
-    return [np.asarray(tab[f"c{i}"], dtype=np.float64).reshape(-1) for i in range(nfield)]
+    cols = [np.asarray(tab[f"c{i}"], dtype=np.float64).reshape(-1) for i in range(nfield)]
+    return (cols, h1) if with_header else cols
 
 
 def read_pixwin_fits(path: str):

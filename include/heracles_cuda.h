@@ -232,6 +232,16 @@ int hcu_ipc_export(hcu_ctx *ctx, const void *ptr, void *handle64);
 int hcu_ipc_open(hcu_ctx *ctx, const void *handle64, void **ptr);
 int hcu_ipc_close(hcu_ctx *ctx, void *ptr);
 
+/* ---- catalogue -> alm without pixels --------------------------------------- */
+/* DiscreteMapper.map_values (heracles/ducc.py:92-133): alm[c] += ducc0.sht.adjoint_synthesis_general(map=values,
+ * spin, lmax, loc=(radians(90 - lat), radians(lon % 360))), i.e. alm_lm += sum_i v_i conj(sY_lm(theta_i, phi_i)),
+ * summed EXACTLY by the Legendre analysis kernels with every point as a ring of its own (O(npts lmax^2); ducc uses a
+ * NUFFT with epsilon 1e-12).  lon / lat in degrees, values[c * value_stride + i], host or device; alm rows
+ * (complex128, healpy order) device accessible; spin 2: rows are (Q, U) pairs -> (E, B). */
+int hcu_points2alm(hcu_ctx *ctx, int lmax, int spin, int ncomp, int64_t npts, const double *lon,
+                   const double *lat, const double *values, int64_t value_stride, void *alm,
+                   int64_t alm_stride);
+
 /* ---- alm -> Cl ------------------------------------------------------------ */
 /* alm2cl(alm, alm2, lmax=lmax) -- heracles/twopoint.py:63-101, as a block:
  *   cl[(i*nb + j)*(lout+1) + l] = sum_m (2 - delta_m0) Re(a_i,lm conj b_j,lm) / (2l+1),

@@ -56,6 +56,23 @@ def test_isinstance_of_the_reference_protocol(ref, mapper):
     assert (mapper.nside, mapper.lmax, mapper.deconvolve) == (64, 100, False)
 
 
+def test_discrete_mapper_satisfies_the_protocol(ref):
+    """heracles/ducc.py:40-162: same constructor keywords (minus nthreads), properties and methods; isinstance of Mapper"""
+    import heracles_b200 as hb
+
+    m = hb.CudaDiscreteMapper(30)
+    assert isinstance(m, ref["mapper"].Mapper)
+    assert (m.lmax, m.area) == (30, 1.0)
+    src = open(os.path.join(REF, "heracles", "ducc.py")).read()
+    cls = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "DiscreteMapper")
+    for fn in (n for n in cls.body if isinstance(n, ast.FunctionDef) and not n.name.startswith("_")):
+        assert hasattr(hb.CudaDiscreteMapper, fn.name), fn.name
+        if fn.name in ("create", "map_values", "transform", "resample"):
+            ours = [p for p in inspect.signature(getattr(hb.CudaDiscreteMapper, fn.name)).parameters]
+            assert ours == [a.arg for a in fn.args.args] + ([fn.args.vararg.arg] if fn.args.vararg else []) + [a.arg for a in fn.args.kwonlyargs] or \
+                sorted(ours) == sorted([a.arg for a in fn.args.args] + ([fn.args.vararg.arg] if fn.args.vararg else []) + [a.arg for a in fn.args.kwonlyargs]), fn.name
+
+
 def test_constructor_and_method_signatures_match_healpixmapper(ref):
     """heracles/healpy.py cannot be imported (healpy), so its class is read from the source"""
     import heracles_b200 as hb
