@@ -50,6 +50,21 @@ constexpr int NT = 32 * NW;
 constexpr int FLS = 34;      // column stride of a flush tile (32 l + 2: conflict free)
 
 
+// EXPERIMENT (-DHCU_PINGPONG, off): ping-pong of the two warps that share an SM sub-partition (warps w and w + 4).  The
+// idea: left alone, the scheduler alternates their DMMAs one by one, so both finish the tensor part of a sub-chunk at the
+// same moment and walk through the hand-over (coefficient wait, votes, rescaling, flush) together while the FP64 pipe
+// idles; with a token (named barriers 1..8, bar.sync on my own, bar.arrive on the partner's) one warp streams its 64
+// DMMAs while the other is in its hand-over.  Measured (nside 2048, spin 2, 4 fields): analysis 149.2 -> 157.5 ms,
+// synthesis 74.9 -> 75.9 ms -- SLOWER: a warp that has the pipe to itself needs ~27 clocks per DMMA of this
+// instruction mix, i.e. the two warps of a sub-partition already overlap little more than their hand-overs.
+#ifdef HCU_PINGPONG
+__device__ __forceinline__ void pp_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pp_pass(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+#else
+__device__ __forceinline__ void pp_wait(int) {}
+__device__ __forceinline__ void pp_pass(int) {}
+#endif
+
 // st.shared.v2.f64 of (a, b) when ok, of zeros otherwise
 __device__ __forceinline__ void sts2_pred1(unsigned addr, double a, double b, int ok) {
   asm volatile(
@@ -384,6 +399,8 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
     mbar_init(mbar + 1, NW);
   }
   __syncthreads();
+  const int pp_my = 1 + 2 * (warp & 3) + (warp >> 2), pp_other = 1 + 2 * (warp & 3) + (1 - (warp >> 2));
+  if (warp >= 4) pp_pass(pp_other);  // the first turn belongs to warps 0..3
 
   // ---- B fragments of this warp's 32 rings, both parities, resident in registers ----
   double bf[8][NJ][2][NBLK];
@@ -518,6 +535,7 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
         rec.begin_sub();
         if (sidx + 1 < nsub) n_rec += 1;
       }
+      pp_wait(pp_my);
       if (live_cur) {
         chunk_live = true;
         n_acc += 1;
@@ -556,7 +574,9 @@ __global__ void __launch_bounds__(NT, 1) legendre_analysis_kernel(LegArgs a) {
 #endif
 
         }
-      } else if (prod) {
+      }
+      pp_pass(pp_other);
+      if (!live_cur && prod) {
 #pragma unroll
         for (int s = 0; s < SL; s += 4) rec.step4(tnxt, ccur, ring, pb, s);
       }
@@ -691,6 +711,8 @@ __global__ void __launch_bounds__(NT, 1) legendre_synthesis_kernel(LegArgs a) {
 
   const int ring = lane;
   bool live_cur = false, live_nxt = false;
+  const int pp_my = 1 + 2 * (warp & 3) + (warp >> 2), pp_other = 1 + 2 * (warp & 3) + (1 - (warp >> 2));
+  if (warp >= 4) pp_pass(pp_other);  // the first turn belongs to warps 0..3
   // ---- prologue: the first sub-chunk and the a_lm of chunk chk0 (chunk 0 without a start-state table) ----
   const int chk0 = st.chk0, s0 = 2 * st.chk0;
   fetch_alm(st.l0 + chk0 * LC);
@@ -724,6 +746,7 @@ __global__ void __launch_bounds__(NT, 1) legendre_synthesis_kernel(LegArgs a) {
         live_nxt = rec.sub_live(sidx + 1);
         rec.begin_sub();
       }
+      pp_wait(pp_my);
       if (live_cur) {
         // k4 steps: (parity p, half h) -> rows p*16 + sb*8 + 4h + fa of btile, l index 4h + fa of the tile
 #pragma unroll
@@ -754,7 +777,9 @@ __global__ void __launch_bounds__(NT, 1) legendre_synthesis_kernel(LegArgs a) {
           }
           rec.step4(tnxt, ccur, ring, pb, ph * 4);
         }
-      } else if (prod) {
+      }
+      pp_pass(pp_other);
+      if (!live_cur && prod) {
 #pragma unroll
         for (int s = 0; s < SL; s += 4) rec.step4(tnxt, ccur, ring, pb, s);
       }
