@@ -313,19 +313,27 @@ class PeerExchange:
         if not chunks:
             return
         cur = torch.cuda.current_stream()
-        if not hasattr(self, "_copy_streams"):
-            self._copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(4)]
+        nstreams = int(os.environ.get("HCU_PUSH_STREAMS", "4"))
+        if not hasattr(self, "_copy_streams") or len(self._copy_streams) != nstreams:
+            self._copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(nstreams)]
         ev = torch.cuda.Event()
         ev.record(cur)
-        used = []
-        for i, (d, off, n, addr) in enumerate(chunks):
-            st = self._copy_streams[i % len(self._copy_streams)]
-            if st not in used:
-                st.wait_event(ev)
-                used.append(st)
-            dst = torch.as_tensor(_CudaView(addr, (n,), "<f8"), device=self.device)
-            with torch.cuda.stream(st):
-                dst.copy_(src[off:off + n], non_blocking=True)
+        # one copy engine does not fill the NVLink ports: every destination's chunk is cut so that about as many copies
+        # as there are side streams are in flight
+        parts = max(1, nstreams // len(chunks))
+        used, i = [], 0
+        for d, off, n, addr in chunks:
+            step = -(-n // parts)
+            for o in range(0, n, step):
+                m = min(step, n - o)
+                st = self._copy_streams[i % nstreams]
+                i += 1
+                if st not in used:
+                    st.wait_event(ev)
+                    used.append(st)
+                dst = torch.as_tensor(_CudaView(addr + 8 * o, (m,), "<f8"), device=self.device)
+                with torch.cuda.stream(st):
+                    dst.copy_(src[off + o:off + o + m], non_blocking=True)
         for st in used:
             done = torch.cuda.Event()
             done.record(st)
