@@ -548,9 +548,9 @@ __global__ void cap_fft_inv_big_kernel(int ilo, int Mh, i64 nside, const double2
   }
 }
 
-int bluestein_M(int i) {
+int bluestein_M(int i) {  // at least 16: the second generation's middle pass works on 16 points
   int need = 2 * i - 1;
-  int M = 2;
+  int M = 16;
   while (M < need) M <<= 1;
   return M;
 }
@@ -728,7 +728,7 @@ static int old_caps_inverse(hcu_ctx *ctx, hcu_geom *g, int lmax, int ncomp, cons
 }
 
 // split of the cap ring pairs [cap_lo, cap_hi) between the generations: the second generation takes north ring
-// numbers 5 .. r2_imax (ring pairs [4, r2_imax)), the first generation what lies below and above
+// numbers 1 .. r2_imax (ring pairs [0, r2_imax)), the first generation what lies above (a_lo..a_hi stays empty)
 struct cap_split {
   i64 a_lo, a_hi;  // first generation, tiny rings
   i64 n_lo, n_hi;  // second generation
@@ -738,12 +738,12 @@ struct cap_split {
 static cap_split split_caps(const hcu_geom *g, i64 cap_lo, i64 cap_hi) {
   cap_split s;
   const i64 imax = g->r2_imax;
-  if (imax < 5) {
+  if (imax < 1) {
     s.a_lo = cap_lo, s.a_hi = cap_hi;
     s.n_lo = s.n_hi = s.b_lo = s.b_hi = cap_hi;
   } else {
-    s.a_lo = cap_lo, s.a_hi = std::min<i64>(cap_hi, 4);
-    s.n_lo = std::max<i64>(cap_lo, 4), s.n_hi = std::min<i64>(cap_hi, imax);
+    s.a_lo = s.a_hi = cap_lo;
+    s.n_lo = cap_lo, s.n_hi = std::min<i64>(cap_hi, imax);
     s.b_lo = std::max<i64>(cap_lo, imax), s.b_hi = cap_hi;
   }
   if (s.a_lo > s.a_hi) s.a_hi = s.a_lo;

@@ -1,8 +1,8 @@
 // k_ringfft2.cu -- second-generation ring FFT stage: ONE fused kernel per ring-pair class and direction.
 //
 // Replaces the FFT half of hp.map2alm / hp.alm2map (heracles/healpy.py:183-189) for every ring pair whose
-// sub-transform fits one CTA (equatorial belt at nside >= 16, polar-cap rings 5 <= i <= 4096); k_ringfft.cu keeps
-// the first generation for the rest (tiny rings, the two-half Bluestein of nside 8192) and as HCU_RINGFFT_GEN=1.
+// sub-transform fits one CTA (equatorial belt at nside >= 16, polar-cap rings i <= 4096); k_ringfft.cu keeps
+// the first generation for the rest (nside < 16 belts, the two-half Bluestein of nside 8192) and as HCU_RINGFFT_GEN=1.
 //
 // A ring pair (north ring + southern mirror, n = 4 L pixels each; L = ring number in the caps, nside in the belt)
 // is ONE complex sequence z = N + i S.  A decimation-in-frequency radix-4 step at load time,
@@ -555,7 +555,7 @@ int tw2_size(int p) {
 }
 
 int bluestein_M2(int i) {
-  int need = 2 * i - 1, M = 2;
+  int need = 2 * i - 1, M = 16;
   while (M < need) M <<= 1;
   return M;
 }
@@ -630,7 +630,7 @@ int launch_group(hcu_ctx *ctx, R2Args &A, int Lmax) {
 
 }  // namespace
 
-// largest cap ring number the second generation handles (0: none); ring numbers below 5 stay with the first generation
+// largest cap ring number the second generation handles (0: none)
 int hcu_ring2_imax(const hcu_geom *g) { return g->r2_imax; }
 
 int hcu_ring2_build(hcu_ctx *ctx, hcu_geom *g, int cap_max_m) {
@@ -657,9 +657,9 @@ int hcu_ring2_build(hcu_ctx *ctx, hcu_geom *g, int cap_max_m) {
     g->r2_belt = true;
   }
   int imax = 0;
-  for (int i = 5; i < nside; ++i)
+  for (int i = 1; i < nside; ++i)
     if (bluestein_M2(i) <= cap_max_m && bluestein_M2(i) <= 8192) imax = i;
-  if (imax >= 5) {
+  if (imax >= 1) {
     const size_t n = (size_t)imax * (imax + 1) / 2;
     HCU_CUDA(cudaMalloc(&g->r2_chirp, sizeof(double2) * n));
     HCU_CUDA(cudaMalloc(&g->r2_wtab, sizeof(double2) * n));
@@ -678,7 +678,7 @@ void hcu_ring2_free(hcu_geom *g) {
   g->r2_tw = g->r2_wbelt = g->r2_chirp = g->r2_wtab = nullptr;
 }
 
-// ring pairs [rp_a, rp_b) of the caps (north ring numbers rp + 1 in 5 .. r2_imax) or of the belt;
+// ring pairs [rp_a, rp_b) of the caps (north ring numbers rp + 1 in 1 .. r2_imax) or of the belt;
 // inverse == false: maps -> phase rows (mlist, nm), inverse == true: phase rows (mpos) -> maps
 int hcu_ring2_run(hcu_ctx *ctx, hcu_geom *g, bool inverse, bool belt, int lmax, int ncomp, const hcu_ptrs &maps,
                   const double *ring_weights, i64 rp_lo, i64 nrp_local, i64 rp_a, i64 rp_b, const int32_t *mlist,
@@ -716,7 +716,7 @@ int hcu_ring2_run(hcu_ctx *ctx, hcu_geom *g, bool inverse, bool belt, int lmax, 
   // two launches: the rings of the largest Bluestein length (one CTA per SM), then everything below it with the
   // largest rings first -- every ring costs the same 32 (lmax + 1) bytes of phase rows, however small it is
   const int itop = (int)rp_b, ifirst = (int)rp_a + 1;
-  const int Mtop = bluestein_M2(itop) < 16 ? 16 : bluestein_M2(itop);
+  const int Mtop = bluestein_M2(itop);
   int il = itop;
   while (il - 1 >= ifirst && bluestein_M2(il - 1) == Mtop) --il;
   A.Mmax = Mtop;
@@ -725,7 +725,7 @@ int hcu_ring2_run(hcu_ctx *ctx, hcu_geom *g, bool inverse, bool belt, int lmax, 
   HCU_CHECK((inverse ? launch_group<true, true>(ctx, A, itop) : launch_group<true, false>(ctx, A, itop)));
   if (il > ifirst) {
     const int i2 = il - 1;
-    A.Mmax = bluestein_M2(i2) < 16 ? 16 : bluestein_M2(i2);
+    A.Mmax = bluestein_M2(i2);
     A.ihi = i2;
     A.nrings = i2 - ifirst + 1;
     HCU_CHECK((inverse ? launch_group<true, true>(ctx, A, i2) : launch_group<true, false>(ctx, A, i2)));
