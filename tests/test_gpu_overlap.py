@@ -37,7 +37,7 @@ def test_overlapped_transform_matches_transform(hb):
         assert a.shape == r.shape
         assert np.linalg.norm(a - r) <= 1e-12 * np.linalg.norm(r), key
         assert (alms[key].dtype.metadata or {}).get("spin") == (0 if key[0] == "POS" else 2)
-    # the mapping context is back on its own stream and still works
+    # both contexts are back on their own streams and still work
     m = mapper.create(spin=0)
     mapper.map_values(np.array([10.0]), np.array([20.0]), m, np.array([2.0]))
     assert float(np.asarray(m).sum()) == 2.0
