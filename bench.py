@@ -1020,6 +1020,17 @@ def main():
         "share_of_step": stats["map_ms"] / total_ms,
     }
 
+    # ring FFT stage (HBM-bound): per component and pass 8 npix bytes of map + 32 nrp (lmax + 1) bytes of phase rows;
+    # (1 + niter) analysis and niter synthesis passes; at N > 1 every rank does its ring-pair block (1 / N of it)
+    ncomp_maps = cfg["nbins"] * (3 if cfg["she"] else 1)
+    fft_bytes = (8.0 * 12 * cfg["nside"] ** 2 + 32.0 * 2 * cfg["nside"] * (cfg["lmax"] + 1)) * ncomp_maps * (1 + 2 * args.niter) / world
+    fft_gbs = fft_bytes / (stats["fft_ms"] / args.steps * 1e-3) / 1e9 if stats["fft_ms"] else None
+    roofline_fft = {
+        "kernel": "ring2_kernel (fused ring FFT, k_ringfft2.cu)", "bound": "hbm", "achieved": fft_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "frac": fft_gbs / hbm_peak if fft_gbs else None, "bytes": "algorithmic: 8 npix + 32 nrp (lmax + 1) per component and pass",
+        "share_of_step": stats["fft_ms"] / total_ms,
+    }
+
     line = {
         "metric": METRIC, "value": ms_per_step / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
@@ -1028,6 +1039,7 @@ def main():
         "stage_ms_per_step": {k: stats[k] / args.steps for k in ("map_ms", "norm_ms", "sht_ms", "cl_ms", "fft_ms", "leg_ana_ms", "leg_syn_ms")},
         "sht_fp64_tflops_nominal": nominal_sht_flops(cfg, args.niter) / (stats["sht_ms"] / args.steps * 1e-3) / 1e12 if stats["sht_ms"] else None,
         "roofline": roofline, "roofline_synthesis": roofline_syn, "roofline_map_values": roofline_map,
+        "roofline_ringfft": roofline_fft,
         "gpu_launches": int((l1[0] - l0[0]) + (l1[1] - l0[1])),
         "gpu_launches_detail": {"own_kernels": int(l1[0] - l0[0]), "cufft_execs": int(l1[1] - l0[1])},
         "clocks": clocks, "checksum": checksum,

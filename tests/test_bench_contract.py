@@ -40,5 +40,7 @@ def test_b200_arm_line():
     assert r["frac"] == pytest.approx(r["achieved"] / r["peak"]) and 0 < r["frac"] < 1 and "traffic" in r
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["unit"] == d["unit"]
+    f = d["roofline_ringfft"]
+    assert f["bound"] == "hbm" and f["unit"] == "GB/s" and 0 < f["frac"] < 1
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
