@@ -261,6 +261,9 @@ class PeerExchange:
     PER_MAX = 48  # doubles per (m, ring pair): 12 components x 4
 
     def __init__(self, ctx, plan, rank, group=None, device=None):
+        """Collective: every rank of `group` must call it.  No rank is left waiting in a collective the others never
+        reach when the allocation or cudaIpcOpenMemHandle fails somewhere: every step that can fail locally is followed
+        by an exchange in which all ranks take part, and a failure anywhere raises on every rank."""
         import torch
         import torch.distributed as dist
 
@@ -268,31 +271,46 @@ class PeerExchange:
 
         self.ctx, self.plan, self.rank, self.group = ctx, plan, int(rank), group
         self.device = device
+        self.base, self.ptr, self._opened, self.stage = 0, [], [], 0
         W = plan.world
         lo, hi = plan.rp_range(rank)
         n_ana = len(plan.mlists[rank]) * plan.nrp * self.PER_MAX      # what the Legendre analysis of this rank reads
         n_syn = (plan.lmax + 1) * (hi - lo) * self.PER_MAX             # what the inverse ring FFTs of this rank read
         self.half_elems = max(n_ana, n_syn, 1)
-        self.base = ctx.malloc_device(2 * self.half_elems * 8)
-        handle = (ctypes.c_ubyte * 64)()
-        _lib.check(ctx.lib.hcu_ipc_export(ctx.handle, ctypes.c_void_p(self.base), handle))
-        mine = (bytes(handle), self.half_elems)
+        mine, err = None, None
+        try:
+            self.base = ctx.malloc_device(2 * self.half_elems * 8)
+            handle = (ctypes.c_ubyte * 64)()
+            _lib.check(ctx.lib.hcu_ipc_export(ctx.handle, ctypes.c_void_p(self.base), handle))
+            mine = (bytes(handle), self.half_elems)
+        except Exception as e:  # noqa: BLE001 - reported after the exchange
+            err = e
         everyone = [None] * W
         dist.all_gather_object(everyone, mine, group=group)
-        self.ptr, self._opened = [], []
-        for d, (h, n) in enumerate(everyone):
-            if d == rank:
-                b = self.base
-            else:
-                p = ctypes.c_void_p()
-                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
-                _lib.check(ctx.lib.hcu_ipc_open(ctx.handle, buf, ctypes.byref(p)))
-                b = p.value
-                self._opened.append(b)
-            self.ptr.append((b, b + 8 * n))
-        self.stage = 0
-        self.flag = torch.zeros(1, dtype=torch.float32, device=device)
-        dist.barrier(group=group)  # every rank has opened every buffer before anybody writes
+        if err is None and any(x is None for x in everyone):
+            err = RuntimeError("another rank could not export its exchange buffer")
+        if err is None:
+            try:
+                for d, (h, n) in enumerate(everyone):
+                    if d == rank:
+                        b = self.base
+                    else:
+                        p = ctypes.c_void_p()
+                        buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                        _lib.check(ctx.lib.hcu_ipc_open(ctx.handle, buf, ctypes.byref(p)))
+                        b = p.value
+                        self._opened.append(b)
+                    self.ptr.append((b, b + 8 * n))
+            except Exception as e:  # noqa: BLE001
+                err = e
+        # every rank has opened every buffer before anybody writes -- or nobody uses the exchange
+        self.flag = torch.tensor([0.0 if err is None else 1.0], dtype=torch.float32, device=device)
+        dist.all_reduce(self.flag, group=group)
+        failed = float(self.flag.item()) != 0.0
+        self.flag.zero_()
+        if failed:
+            self.close()
+            raise RuntimeError(f"peer-memory exchange unavailable: {err or 'a peer could not open the buffers'}")
 
     def next_half(self) -> int:
         h = self.stage & 1
@@ -682,9 +700,6 @@ def attach_peers(lanes, ctx_of, plan, rank, device):
     devices) every rank falls back to the NCCL exchange together"""
     import warnings
 
-    import torch
-    import torch.distributed as dist
-
     if plan.world <= 1 or exchange_mode() != "peer":
         return lanes
     for lane in lanes:
@@ -696,21 +711,11 @@ def attach_peers(lanes, ctx_of, plan, rank, device):
         if key in _PEER_CACHE:
             lane.peers = _PEER_CACHE[key]
             continue
-        ex, ok = None, 1
-        try:
-            ex = PeerExchange(ctx, plan, rank, group=lane.group, device=device)
-        except Exception as e:  # noqa: BLE001 - reported below, on every rank
-            ok, err = 0, e
-        flag = torch.tensor([ok], dtype=torch.int32, device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=lane.group)
-        if int(flag.item()) == 1:
-            lane.peers = _PEER_CACHE[key] = ex
-        else:
+        try:  # (collective; fails on every rank together)
+            lane.peers = _PEER_CACHE[key] = PeerExchange(ctx, plan, rank, group=lane.group, device=device)
+        except RuntimeError as e:
             _PEER_CACHE[key] = None
-            if ex is not None:
-                ex.close()
-            if not ok:
-                warnings.warn(f"peer-memory exchange unavailable ({err}); using the NCCL all-to-all", stacklevel=2)
+            warnings.warn(f"{e}; using the NCCL all-to-all", stacklevel=2)
     return lanes
 
 
