@@ -570,9 +570,13 @@ template <bool BLU, bool INV>
 int launch_group(hcu_ctx *ctx, R2Args &A, int Lmax) {
   int NT = ring2_threads(A.Mmax);
   int occ_cap = 3;  // more resident CTAs only push the scratch out of the L2
-  if (!BLU) {       // tuning knobs of the belt launch
+  // tuning knobs: threads per CTA of the belt launch / of the cap launch below the largest Bluestein length
+  if (!BLU) {
+    if (A.Mmax >= 4096) NT = 512;  // measured at nside 4096: one 512-thread CTA per SM beats two of 256 (emission and loads use all threads)
     if (const char *e = getenv("HCU_R2_BELT_NT")) NT = atoi(e) >= 32 && atoi(e) <= 512 ? atoi(e) : NT;
     if (const char *e = getenv("HCU_R2_BELT_OCC")) occ_cap = atoi(e) >= 1 ? atoi(e) : occ_cap;
+  } else if (A.Mmax < 8192) {
+    if (const char *e = getenv("HCU_R2_REST_NT")) NT = atoi(e) >= 32 && atoi(e) <= 512 ? atoi(e) : NT;
   }
   const size_t smem = sizeof(double2) * (size_t)(A.Mmax + (A.Mmax >> 4) + tw2_size(ilog2_host(A.Mmax)));
   HCU_CUDA(cudaFuncSetAttribute(ring2_kernel<BLU, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
