@@ -63,6 +63,10 @@ extern "C" int hcu_create(int device, hcu_ctx **out) {
   hcu_ctx *ctx = new hcu_ctx();
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
+  if (const char *e = getenv("HCU_SLOT_ROWS")) {
+    const long long v = atoll(e);
+    if (v >= (1 << 12) && v <= (1 << 24)) ctx->SLOT_ROWS = v;
+  }
   HCU_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
   HCU_CUDA(cudaMalloc(&ctx->bad_rows, sizeof(unsigned long long)));
@@ -291,7 +295,7 @@ static int ensure_slots(hcu_ctx *ctx) {
   for (int i = 0; i < hcu_ctx::NSLOT; ++i) {
     hcu_stage_slot &s = ctx->slot[i];
     if (s.dev) continue;
-    size_t bytes = sizeof(double) * hcu_ctx::SLOT_ROWS * hcu_ctx::SLOT_COLS;
+    size_t bytes = sizeof(double) * ctx->SLOT_ROWS * hcu_ctx::SLOT_COLS;
     HCU_CUDA(cudaHostAlloc(&s.host, bytes, cudaHostAllocDefault));
     HCU_CUDA(cudaMalloc(&s.dev, bytes));
     HCU_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -329,12 +333,12 @@ static int stage_column(hcu_ctx *ctx, hcu_stage_slot &s, int col, const double *
     *dev = src + r0;
     return HCU_OK;
   }
-  double *d = s.dev + (i64)col * hcu_ctx::SLOT_ROWS;
+  double *d = s.dev + (i64)col * ctx->SLOT_ROWS;
   // the copies run on their own stream so that they overlap the scatter kernel of the previous chunk
   if (kind == PK_PINNED) {
     HCU_CUDA(cudaMemcpyAsync(d, src + r0, sizeof(double) * nr, cudaMemcpyHostToDevice, ctx->copy_stream));
   } else {
-    double *h = s.host + (i64)col * hcu_ctx::SLOT_ROWS;
+    double *h = s.host + (i64)col * ctx->SLOT_ROWS;
     parallel_memcpy(h, src + r0, sizeof(double) * nr);
     HCU_CUDA(cudaMemcpyAsync(d, h, sizeof(double) * nr, cudaMemcpyHostToDevice, ctx->copy_stream));
   }
@@ -354,8 +358,8 @@ static int map_values_impl(hcu_ctx *ctx, i64 nside, int scheme, const double *lo
                                  mstride, flags, ipix_dev);
   HCU_ARG(nv <= hcu_ctx::SLOT_COLS - 2, "at most 2 value rows when staging host pages");
   HCU_CHECK(ensure_slots(ctx));
-  for (i64 r0 = 0; r0 < n; r0 += hcu_ctx::SLOT_ROWS) {
-    const i64 nr = std::min<i64>(hcu_ctx::SLOT_ROWS, n - r0);
+  for (i64 r0 = 0; r0 < n; r0 += ctx->SLOT_ROWS) {
+    const i64 nr = std::min<i64>(ctx->SLOT_ROWS, n - r0);
     hcu_stage_slot &s = ctx->slot[ctx->next_slot];
     ctx->next_slot = (ctx->next_slot + 1) % hcu_ctx::NSLOT;
     if (s.used) HCU_CUDA(cudaEventSynchronize(s.done));  // slot (pinned + device buffer) free again
@@ -371,8 +375,8 @@ static int map_values_impl(hcu_ctx *ctx, i64 nside, int scheme, const double *lo
           const double *tmp;
           HCU_CHECK(stage_column(ctx, s, 2 + v, values + (i64)v * vstride, kval, r0, nr, &tmp));
         }
-        dval = s.dev + 2 * hcu_ctx::SLOT_ROWS;
-        dvstride = hcu_ctx::SLOT_ROWS;
+        dval = s.dev + 2 * ctx->SLOT_ROWS;
+        dvstride = ctx->SLOT_ROWS;
       }
     }
     HCU_CUDA(cudaEventRecord(s.ready, ctx->copy_stream));
@@ -416,8 +420,8 @@ extern "C" int hcu_map_page(hcu_ctx *ctx, int64_t nside, int scheme, const doubl
   }
   if (direct) return hcu_launch_map_page(ctx, nside, scheme, lon, lat, w, col[3], col[4], n, pos, she, she_stride, stats);
   HCU_CHECK(ensure_slots(ctx));
-  for (i64 r0 = 0; r0 < n; r0 += hcu_ctx::SLOT_ROWS) {
-    const i64 nr = std::min<i64>(hcu_ctx::SLOT_ROWS, n - r0);
+  for (i64 r0 = 0; r0 < n; r0 += ctx->SLOT_ROWS) {
+    const i64 nr = std::min<i64>(ctx->SLOT_ROWS, n - r0);
     hcu_stage_slot &s = ctx->slot[ctx->next_slot];
     ctx->next_slot = (ctx->next_slot + 1) % hcu_ctx::NSLOT;
     if (s.used) HCU_CUDA(cudaEventSynchronize(s.done));

@@ -138,7 +138,7 @@ struct hcu_ctx {
   i64 n_launch = 0, n_cufft = 0;
   // staging for pageable host pages
   static const int NSLOT = 3;
-  static const i64 SLOT_ROWS = 1 << 19;
+  i64 SLOT_ROWS = 1 << 20;  // rows per staging slot (HCU_SLOT_ROWS at hcu_create); measured 47.5 / 50.8 / 53.1 / 53.2 GB/s host to map at 2^18 .. 2^21
   static const int SLOT_COLS = 5; // lon, lat, up to 3 more columns (hcu_map_values: 2 value rows; hcu_map_page: w, g1, g2)
   hcu_stage_slot slot[NSLOT];
   int next_slot = 0;
